@@ -1,0 +1,203 @@
+/*
+ * mrgs.h — C ABI of libmrgs.so, the B200-native (sm_100a) surfel-splatting render path.
+ *
+ * This library is a drop-in for the compute side of MaterialRefGS's
+ * submodules/diff-surfel-rasterization and of the split-sum deferred shading in
+ * utils/refl_utils.py + scene/light.py + scene/renderutils (cubemap prefilter).
+ *
+ * Conventions
+ *   - every pointer is a raw DEVICE pointer unless the field name starts with `host_`;
+ *   - all arithmetic data is fp32, ids/counters are 32-bit, sort keys 64-bit;
+ *   - matrices use the reference's row-vector convention: the 16 floats are indexed
+ *     m[col*4+row] (rast/cuda_rasterizer/auxiliary.h:80-99);
+ *   - every entry point takes the CUDA stream to launch on (`void*` == cudaStream_t) and
+ *     returns an int status: 0 = ok, MRGS_ERR_* otherwise. `mrgs_last_error()` returns a
+ *     human-readable message for the calling thread;
+ *   - no torch types cross this boundary; scratch memory is owned by the caller.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference root,
+ * rast/ = submodules/diff-surfel-rasterization/):
+ *   mrgs_forward        <- CudaRasterizer::Rasterizer::forward   rast/cuda_rasterizer/rasterizer.h:33,
+ *                          called from RasterizeGaussiansCUDA      rast/rasterize_points.cu:41-144
+ *   mrgs_backward       <- CudaRasterizer::Rasterizer::backward  rast/cuda_rasterizer/rasterizer.h:61,
+ *                          called from RasterizeGaussiansBackwardCUDA rast/rasterize_points.cu:146-252
+ *   mrgs_mark_visible   <- CudaRasterizer::Rasterizer::markVisible rast/cuda_rasterizer/rasterizer.h:26,
+ *                          called from markVisible                 rast/rasterize_points.cu:254-273
+ *   mrgs_*_bytes        <- required<GeometryState/ImageState/BinningState>() rast/cuda_rasterizer/rasterizer_impl.h:68-74
+ *   mrgs_shade_forward/backward <- get_specular_color_surfel utils/refl_utils.py:364-419,
+ *                          EnvLight.get_mip/__call__ scene/light.py:88-129 and the compositing in
+ *                          render_surfel gaussian_renderer/__init__.py:419-445
+ *   mrgs_cubemap_*      <- scene/renderutils/c_src/cubemap.cu:110-354 + scene/light_utils.py:66-80
+ */
+#ifndef MRGS_H_INCLUDED
+#define MRGS_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRGS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define MRGS_API __attribute__((visibility("default")))
+#else
+#define MRGS_API
+#endif
+
+/* compile-time constants of the numerical contract (rast/cuda_rasterizer/config.h:17-20,
+ * auxiliary.h:23-41) */
+#define MRGS_TILE_X 16
+#define MRGS_TILE_Y 16
+#define MRGS_TILE_PIXELS 256
+#define MRGS_MAX_FEATURES 24
+#define MRGS_NUM_CHANNELS 3
+#define MRGS_NUM_OTHERS 7 /* depth, alpha, normal xyz, median depth, distortion */
+
+/* status codes */
+#define MRGS_OK 0
+#define MRGS_ERR_INVALID_ARGUMENT 1
+#define MRGS_ERR_CUDA 2
+#define MRGS_ERR_WORKSPACE 3
+#define MRGS_ERR_UNSUPPORTED 4
+
+/* floats per surfel of the two packed per-surfel records inside the geometry buffer */
+#define MRGS_GEOM_FLOATS 16
+
+/* Allocation callback used for the one scratch buffer whose size is only known after
+ * preprocessing (the number of surfel x tile instances R). Mirrors the reference's
+ * std::function<char*(size_t)> trick (rast/rasterize_points.cu:33-39). Must return a
+ * device pointer aligned to >= 256 bytes that stays valid until the matching backward. */
+typedef void* (*mrgs_alloc_fn)(void* ctx, size_t bytes);
+
+/* Byte offsets of the sub-arrays inside the caller-owned scratch buffers. Exposed so tests
+ * can decode tile keys / sorted ids / ranges / contributor counts bit-for-bit. */
+typedef struct MrgsGeomLayout {
+    size_t rec;           /* float [P][16]: Tu.xyz Tw.x | Tv.xyz Tw.y | Tw.z xy.x xy.y opacity | n.xyz depth */
+    size_t cf;            /* float [P][cf_stride]: rgb(3) features(S) zero padding                       */
+    size_t clamped;       /* uint8 [P]: bit c set when SH colour channel c was clamped to 0             */
+    size_t tiles_touched; /* uint32[P]                                                                    */
+    size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched                              */
+    size_t rect;          /* uint32[P][2]: (min.x | min.y<<16), (max.x | max.y<<16) tile rectangle        */
+    size_t scan_temp;     /* scan scratch                                                                 */
+    size_t scan_temp_bytes;
+    size_t total;         /* bytes required                                                               */
+    int32_t cf_stride;    /* floats per surfel in `cf` (3+S rounded up to a multiple of 4)                */
+} MrgsGeomLayout;
+
+typedef struct MrgsImageLayout {
+    size_t state;     /* float/uint32 [tiles][5][256]: per tile, planes final_T, M1, M2, n_contrib, median_contrib;
+                         pixel slot inside a tile = mrgs pixel order (see mrgs_tile_slot)                */
+    size_t ranges;    /* uint32[tiles][2]                                                                */
+    size_t total;
+} MrgsImageLayout;
+
+typedef struct MrgsBinningLayout {
+    size_t point_list;           /* uint32[R] sorted surfel ids            */
+    size_t point_list_unsorted;  /* uint32[R]                              */
+    size_t keys;                 /* uint64[R] sorted  (tile<<32 | depth)   */
+    size_t keys_unsorted;        /* uint64[R]                              */
+    size_t sort_temp;
+    size_t sort_temp_bytes;
+    size_t total;
+} MrgsBinningLayout;
+
+MRGS_API int mrgs_abi_version(void);
+MRGS_API const char* mrgs_last_error(void);
+
+MRGS_API int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out);
+MRGS_API int mrgs_image_layout(int32_t width, int32_t height, MrgsImageLayout* out);
+MRGS_API int mrgs_binning_layout(int64_t R, MrgsBinningLayout* out);
+MRGS_API size_t mrgs_geom_bytes(int32_t P, int32_t S);
+MRGS_API size_t mrgs_image_bytes(int32_t width, int32_t height);
+MRGS_API size_t mrgs_binning_bytes(int64_t R);
+
+/* Slot (0..255) of pixel (x,y) inside its 16x16 tile in the image-state planes. */
+MRGS_API int mrgs_tile_slot(int32_t x_in_tile, int32_t y_in_tile);
+
+typedef struct MrgsForwardArgs {
+    int32_t P;              /* number of surfels                                        */
+    int32_t S;              /* extra feature channels, 0..MRGS_MAX_FEATURES             */
+    int32_t sh_degree;      /* active SH degree D                                       */
+    int32_t sh_coeffs;      /* M: coefficients per channel in `shs` (0 if no SH)        */
+    int32_t width, height;
+    float tan_fovx, tan_fovy;
+    float scale_modifier;
+    int32_t prefiltered;
+    int32_t debug;          /* !=0: synchronise + check after every launch              */
+    const float* background;       /* [3]                                               */
+    const float* means3D;          /* [P,3]                                             */
+    const float* shs;              /* [P,M,3]  or NULL                                  */
+    const float* colors_precomp;   /* [P,3]    or NULL (exactly one of shs / this)      */
+    const float* features;         /* [P,S]    or NULL when S == 0                      */
+    const float* opacities;        /* [P]                                               */
+    const float* scales;           /* [P,2]    or NULL                                  */
+    const float* rotations;        /* [P,4]    or NULL                                  */
+    const float* transMat_precomp; /* [P,9]    or NULL (exactly one of scale+rot / this)*/
+    const float* viewmatrix;       /* [16]                                              */
+    const float* projmatrix;       /* [16]                                              */
+    const float* campos;           /* [3]                                               */
+    float* out_color;              /* [3,H,W]                                           */
+    float* out_feature;            /* [S,H,W]                                           */
+    float* out_others;             /* [7,H,W]                                           */
+    int32_t* radii;                /* [P]                                               */
+    void* geom_buffer;   size_t geom_bytes;
+    void* image_buffer;  size_t image_bytes;
+    mrgs_alloc_fn binning_alloc;   void* binning_ctx;
+    /* results */
+    int32_t num_rendered;          /* R, also the reference's first return value        */
+    void* binning_buffer;          /* what binning_alloc returned (NULL if R == 0)      */
+} MrgsForwardArgs;
+
+typedef struct MrgsBackwardArgs {
+    int32_t P, S, sh_degree, sh_coeffs, width, height;
+    float tan_fovx, tan_fovy, scale_modifier;
+    int32_t debug;
+    int32_t num_rendered;          /* R from the forward                                */
+    const float* background;
+    const float* means3D;
+    const float* shs;
+    const float* colors_precomp;
+    const float* features;
+    const float* scales;
+    const float* rotations;
+    const float* transMat_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    const int32_t* radii;
+    const void* geom_buffer;
+    const void* binning_buffer;
+    const void* image_buffer;
+    const float* dL_dout_color;    /* [3,H,W]                                           */
+    const float* dL_dout_feature;  /* [S,H,W]                                           */
+    const float* dL_dout_others;   /* [7,H,W]                                           */
+    /* outputs: every element is written by the call (no pre-zeroing needed) */
+    float* dL_dmeans2D;   /* [P,3]  densification proxy in .xy, 0 in .z                 */
+    float* dL_dcolors;    /* [P,3]                                                      */
+    float* dL_dfeatures;  /* [P,S]                                                      */
+    float* dL_dopacity;   /* [P]                                                        */
+    float* dL_dmeans3D;   /* [P,3]                                                      */
+    float* dL_dtransMat;  /* [P,9]                                                      */
+    float* dL_dsh;        /* [P,M,3]                                                    */
+    float* dL_dscales;    /* [P,2]                                                      */
+    float* dL_drotations; /* [P,4]                                                      */
+    /* scratch: raw per-surfel gradient arena, >= mrgs_grad_arena_bytes(P,S) */
+    void* grad_arena;     size_t grad_arena_bytes;
+} MrgsBackwardArgs;
+
+MRGS_API size_t mrgs_grad_arena_bytes(int32_t P, int32_t S);
+/* floats per surfel in the raw gradient arena and the field offsets inside one row */
+MRGS_API int32_t mrgs_grad_arena_stride(int32_t S);
+
+MRGS_API int mrgs_forward(MrgsForwardArgs* args, void* stream);
+MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
+MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, void* stream);
+
+#ifdef __cplusplus
+} /* extern "C" */
+#endif
+#endif /* MRGS_H_INCLUDED */

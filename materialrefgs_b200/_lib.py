@@ -1,0 +1,133 @@
+"""ctypes binding of libmrgs.so — the only place Python touches the C ABI (include/mrgs.h).
+
+There is deliberately no CPU or torch fallback: if the CUDA library is missing the import of
+the product path fails loudly (set MRGS_AUTOBUILD=0 to forbid the in-tree nvcc build).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent
+LIB_PATH = _PKG / "libmrgs.so"
+
+MRGS_ABI_VERSION = 1
+MAX_FEATURES = 24
+TILE = 16
+
+alloc_fn = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class GeomLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "rec", "cf", "clamped", "tiles_touched", "point_offsets", "rect", "scan_temp",
+        "scan_temp_bytes", "total")] + [("cf_stride", C.c_int32)]
+
+
+class ImageLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in ("state", "ranges", "total")]
+
+
+class BinningLayout(C.Structure):
+    _fields_ = [(n, C.c_size_t) for n in (
+        "point_list", "point_list_unsorted", "keys", "keys_unsorted", "sort_temp",
+        "sort_temp_bytes", "total")]
+
+
+_fp = C.c_void_p  # device pointers travel as integers
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("S", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32),
+        ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp),
+        ("features", _fp), ("opacities", _fp), ("scales", _fp), ("rotations", _fp),
+        ("transMat_precomp", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
+        ("out_color", _fp), ("out_feature", _fp), ("out_others", _fp), ("radii", _fp),
+        ("geom_buffer", _fp), ("geom_bytes", C.c_size_t),
+        ("image_buffer", _fp), ("image_bytes", C.c_size_t),
+        ("binning_alloc", alloc_fn), ("binning_ctx", C.c_void_p),
+        ("num_rendered", C.c_int32), ("binning_buffer", _fp),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("S", C.c_int32), ("sh_degree", C.c_int32), ("sh_coeffs", C.c_int32),
+        ("width", C.c_int32), ("height", C.c_int32),
+        ("tan_fovx", C.c_float), ("tan_fovy", C.c_float), ("scale_modifier", C.c_float),
+        ("debug", C.c_int32), ("num_rendered", C.c_int32),
+        ("background", _fp), ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp),
+        ("features", _fp), ("scales", _fp), ("rotations", _fp), ("transMat_precomp", _fp),
+        ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp), ("radii", _fp),
+        ("geom_buffer", _fp), ("binning_buffer", _fp), ("image_buffer", _fp),
+        ("dL_dout_color", _fp), ("dL_dout_feature", _fp), ("dL_dout_others", _fp),
+        ("dL_dmeans2D", _fp), ("dL_dcolors", _fp), ("dL_dfeatures", _fp), ("dL_dopacity", _fp),
+        ("dL_dmeans3D", _fp), ("dL_dtransMat", _fp), ("dL_dsh", _fp), ("dL_dscales", _fp),
+        ("dL_drotations", _fp),
+        ("grad_arena", _fp), ("grad_arena_bytes", C.c_size_t),
+    ]
+
+
+# every symbol include/mrgs.h declares: name -> (restype, argtypes)
+SYMBOLS = {
+    "mrgs_abi_version": (C.c_int, []),
+    "mrgs_last_error": (C.c_char_p, []),
+    "mrgs_geom_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(GeomLayout)]),
+    "mrgs_image_layout": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(ImageLayout)]),
+    "mrgs_binning_layout": (C.c_int, [C.c_int64, C.POINTER(BinningLayout)]),
+    "mrgs_geom_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mrgs_image_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mrgs_binning_bytes": (C.c_size_t, [C.c_int64]),
+    "mrgs_tile_slot": (C.c_int, [C.c_int32, C.c_int32]),
+    "mrgs_grad_arena_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mrgs_grad_arena_stride": (C.c_int32, [C.c_int32]),
+    "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
+    "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
+    "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
+}
+
+_lib = None
+
+
+class MrgsError(RuntimeError):
+    """Raised for any non-zero status returned by libmrgs (the reference raises RuntimeError
+    from AT_ERROR / std::runtime_error, rast/rasterize_points.cu:62-64)."""
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if os.environ.get("MRGS_AUTOBUILD", "1") != "0":
+        from . import build as _build
+        if not _build.is_current():
+            try:
+                _build.build()
+            except Exception as ex:  # stale-but-present library is still usable on a box without nvcc
+                if not LIB_PATH.exists():
+                    raise ImportError(f"libmrgs.so is missing and could not be built: {ex}") from ex
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found. Build it with `python -m materialrefgs_b200.build`; "
+            "there is no CPU fallback for the render path.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def last_error() -> str:
+    return load().mrgs_last_error().decode("utf-8", "replace")
+
+
+def check(status: int, what: str) -> None:
+    if status != 0:
+        raise MrgsError(f"{what} failed (status {status}): {last_error()}")

@@ -1,0 +1,376 @@
+// api.cu — extern "C" entry points of libmrgs.so (see include/mrgs.h for the contract and the
+// reference interface each one replaces).
+#include <stdarg.h>
+#include <string.h>
+
+#include "kernels.cuh"
+
+namespace mrgs {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what, cudaStream_t stream, bool debug) {
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && debug) e = cudaStreamSynchronize(stream);
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return MRGS_ERR_CUDA;
+    }
+    return MRGS_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+// pinned host slot for the one scalar that has to reach the host (R)
+static int32_t* pinned_slot() {
+    static thread_local int32_t* slot = nullptr;
+    if (slot == nullptr) {
+        if (cudaHostAlloc((void**)&slot, 64, cudaHostAllocDefault) != cudaSuccess) slot = nullptr;
+    }
+    return slot;
+}
+
+}  // namespace mrgs
+
+using namespace mrgs;
+
+extern "C" {
+
+int mrgs_abi_version(void) { return MRGS_ABI_VERSION; }
+const char* mrgs_last_error(void) { return g_error; }
+int mrgs_tile_slot(int32_t x, int32_t y) { return slot_of(x, y); }
+int32_t mrgs_grad_arena_stride(int32_t S) { return grad_stride(S); }
+size_t mrgs_grad_arena_bytes(int32_t P, int32_t S) {
+    return align_up((size_t)P * grad_stride(S) * sizeof(float));
+}
+
+int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out) {
+    if (out == nullptr || P < 0 || S < 0 || S > MRGS_MAX_FEATURES) {
+        set_error("mrgs_geom_layout: bad arguments (P=%d, S=%d)", P, S);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n = (size_t)P;
+    size_t off = 0;
+    out->cf_stride = cf_stride(S);
+    out->rec = off;           off = align_up(off + n * kGeomFloats * sizeof(float));
+    out->cf = off;            off = align_up(off + n * out->cf_stride * sizeof(float));
+    out->clamped = off;       off = align_up(off + n);
+    out->tiles_touched = off; off = align_up(off + n * sizeof(uint32_t));
+    out->point_offsets = off; off = align_up(off + n * sizeof(uint32_t));
+    out->rect = off;          off = align_up(off + n * sizeof(uint2));
+    out->scan_temp = off;
+    out->scan_temp_bytes = scan_temp_bytes(P > 0 ? P : 1);
+    off = align_up(off + out->scan_temp_bytes);
+    out->total = off;
+    return MRGS_OK;
+}
+
+int mrgs_image_layout(int32_t width, int32_t height, MrgsImageLayout* out) {
+    if (out == nullptr || width <= 0 || height <= 0) {
+        set_error("mrgs_image_layout: bad arguments (%dx%d)", width, height);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const size_t tiles = (size_t)((width + kTileX - 1) / kTileX) * ((height + kTileY - 1) / kTileY);
+    size_t off = 0;
+    out->state = off;  off = align_up(off + tiles * 5 * kTilePixels * sizeof(float));
+    out->ranges = off; off = align_up(off + tiles * sizeof(uint2));
+    out->total = off;
+    return MRGS_OK;
+}
+
+int mrgs_binning_layout(int64_t R, MrgsBinningLayout* out) {
+    if (out == nullptr || R < 0 || R > 0x7fffffff) {
+        set_error("mrgs_binning_layout: bad instance count %lld", (long long)R);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const size_t n = (size_t)R;
+    size_t off = 0;
+    out->point_list = off;          off = align_up(off + n * sizeof(uint32_t));
+    out->point_list_unsorted = off; off = align_up(off + n * sizeof(uint32_t));
+    out->keys = off;                off = align_up(off + n * sizeof(uint64_t));
+    out->keys_unsorted = off;       off = align_up(off + n * sizeof(uint64_t));
+    out->sort_temp = off;
+    out->sort_temp_bytes = sort_temp_bytes(R > 0 ? R : 1);
+    off = align_up(off + out->sort_temp_bytes);
+    out->total = off;
+    return MRGS_OK;
+}
+
+size_t mrgs_geom_bytes(int32_t P, int32_t S) {
+    MrgsGeomLayout l;
+    return mrgs_geom_layout(P, S, &l) == MRGS_OK ? l.total : 0;
+}
+size_t mrgs_image_bytes(int32_t w, int32_t h) {
+    MrgsImageLayout l;
+    return mrgs_image_layout(w, h, &l) == MRGS_OK ? l.total : 0;
+}
+size_t mrgs_binning_bytes(int64_t R) {
+    MrgsBinningLayout l;
+    return mrgs_binning_layout(R, &l) == MRGS_OK ? l.total : 0;
+}
+
+int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present, void* stream_) {
+    (void)projmatrix;  // the reference computes p_hom from it but never uses the result
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) {
+        set_error("mrgs_mark_visible: bad arguments");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return MRGS_OK;
+    launch_mark_visible(P, means3D, viewmatrix, present, stream);
+    MRGS_LAUNCH_OK("mark_visible", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (a == nullptr) {
+        set_error("mrgs_forward: null args");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    a->num_rendered = 0;
+    a->binning_buffer = nullptr;
+    if (a->P < 0 || a->width <= 0 || a->height <= 0) {
+        set_error("mrgs_forward: bad sizes P=%d W=%d H=%d", a->P, a->width, a->height);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->S < 0 || a->S > MRGS_MAX_FEATURES) {
+        set_error("mrgs_forward: S=%d feature channels, supported range is 0..%d", a->S,
+                  MRGS_MAX_FEATURES);
+        return MRGS_ERR_UNSUPPORTED;
+    }
+    if ((a->shs == nullptr) == (a->colors_precomp == nullptr)) {
+        set_error("mrgs_forward: provide exactly one of shs / colors_precomp");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+    if (has_sr == (a->transMat_precomp != nullptr)) {
+        set_error("mrgs_forward: provide exactly one of scales+rotations / transMat_precomp");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->shs != nullptr && a->sh_coeffs < (a->sh_degree + 1) * (a->sh_degree + 1)) {
+        set_error("mrgs_forward: sh_degree %d needs %d coefficients, got %d", a->sh_degree,
+                  (a->sh_degree + 1) * (a->sh_degree + 1), a->sh_coeffs);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->S > 0 && a->features == nullptr) {
+        set_error("mrgs_forward: S=%d but features is null", a->S);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const bool debug = a->debug != 0;
+    const int W = a->width, H = a->height;
+    const int grid_x = (W + kTileX - 1) / kTileX, grid_y = (H + kTileY - 1) / kTileY;
+    const int tiles = grid_x * grid_y;
+    if (grid_x > 0xffff || grid_y > 0xffff) {
+        set_error("mrgs_forward: image too large");
+        return MRGS_ERR_UNSUPPORTED;
+    }
+
+    MrgsImageLayout il;
+    if (mrgs_image_layout(W, H, &il) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+    if (a->image_buffer == nullptr || a->image_bytes < il.total) {
+        set_error("mrgs_forward: image buffer too small (%zu < %zu)", a->image_bytes, il.total);
+        return MRGS_ERR_WORKSPACE;
+    }
+    char* img = (char*)a->image_buffer;
+    uint2* ranges = (uint2*)(img + il.ranges);
+    float* state = (float*)(img + il.state);
+
+    RenderFwdParams rp{};
+    rp.S = a->S; rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y;
+    rp.cf_stride = cf_stride(a->S);
+    rp.ranges = ranges;
+    rp.background = a->background;
+    rp.state = state;
+    rp.out_color = a->out_color;
+    rp.out_feature = a->out_feature;
+    rp.out_others = a->out_others;
+
+    MRGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), stream));
+
+    int R = 0;
+    if (a->P > 0) {
+        MrgsGeomLayout gl;
+        if (mrgs_geom_layout(a->P, a->S, &gl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+        if (a->geom_buffer == nullptr || a->geom_bytes < gl.total) {
+            set_error("mrgs_forward: geometry buffer too small (%zu < %zu)", a->geom_bytes, gl.total);
+            return MRGS_ERR_WORKSPACE;
+        }
+        char* geom = (char*)a->geom_buffer;
+        PreprocessParams pp{};
+        pp.P = a->P; pp.S = a->S; pp.D = a->sh_degree; pp.M = a->sh_coeffs; pp.W = W; pp.H = H;
+        pp.grid_x = grid_x; pp.grid_y = grid_y; pp.cf_stride = gl.cf_stride;
+        pp.scale_modifier = a->scale_modifier; pp.prefiltered = a->prefiltered;
+        pp.means3D = a->means3D; pp.scales = a->scales; pp.rotations = a->rotations;
+        pp.opacities = a->opacities; pp.shs = a->shs; pp.colors_precomp = a->colors_precomp;
+        pp.features = a->features; pp.transMat_precomp = a->transMat_precomp;
+        pp.viewmatrix = a->viewmatrix; pp.projmatrix = a->projmatrix; pp.campos = a->campos;
+        pp.radii = a->radii;
+        pp.rec = (float*)(geom + gl.rec);
+        pp.cf = (float*)(geom + gl.cf);
+        pp.clamped = (uint8_t*)(geom + gl.clamped);
+        pp.tiles_touched = (uint32_t*)(geom + gl.tiles_touched);
+        pp.rect = (uint2*)(geom + gl.rect);
+        uint32_t* offsets = (uint32_t*)(geom + gl.point_offsets);
+
+        launch_preprocess_fwd(pp, stream);
+        MRGS_LAUNCH_OK("preprocess_fwd", stream, debug);
+
+        int st = run_inclusive_scan(pp.tiles_touched, offsets, a->P, geom + gl.scan_temp,
+                                    gl.scan_temp_bytes, stream);
+        if (st != MRGS_OK) return st;
+        MRGS_LAUNCH_OK("scan", stream, debug);
+
+        // R has to reach the host to size the binning buffer (same point as
+        // rasterizer_impl.cu:287, but through pinned memory on the caller's stream)
+        int32_t* slot = pinned_slot();
+        if (slot == nullptr) {
+            set_error("mrgs_forward: cudaHostAlloc failed");
+            return MRGS_ERR_CUDA;
+        }
+        MRGS_CUDA_OK(cudaMemcpyAsync(slot, offsets + a->P - 1, sizeof(int32_t),
+                                     cudaMemcpyDeviceToHost, stream));
+        MRGS_CUDA_OK(cudaStreamSynchronize(stream));
+        R = *slot;
+        if (R < 0) {
+            set_error("mrgs_forward: instance count overflow (R=%d)", R);
+            return MRGS_ERR_UNSUPPORTED;
+        }
+
+        if (R > 0) {
+            MrgsBinningLayout bl;
+            if (mrgs_binning_layout(R, &bl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+            if (a->binning_alloc == nullptr) {
+                set_error("mrgs_forward: binning_alloc callback is null");
+                return MRGS_ERR_INVALID_ARGUMENT;
+            }
+            char* bin = (char*)a->binning_alloc(a->binning_ctx, bl.total);
+            if (bin == nullptr) {
+                set_error("mrgs_forward: binning_alloc(%zu) returned null", bl.total);
+                return MRGS_ERR_WORKSPACE;
+            }
+            a->binning_buffer = bin;
+            uint64_t* keys_unsorted = (uint64_t*)(bin + bl.keys_unsorted);
+            uint64_t* keys = (uint64_t*)(bin + bl.keys);
+            uint32_t* vals_unsorted = (uint32_t*)(bin + bl.point_list_unsorted);
+            uint32_t* vals = (uint32_t*)(bin + bl.point_list);
+
+            launch_duplicate_with_keys(a->P, pp.rec, pp.rect, a->radii, offsets, keys_unsorted,
+                                       vals_unsorted, grid_x, stream);
+            MRGS_LAUNCH_OK("duplicate_with_keys", stream, debug);
+
+            const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);
+            st = run_sort_pairs(keys_unsorted, keys, vals_unsorted, vals, R, end_bit,
+                                bin + bl.sort_temp, bl.sort_temp_bytes, stream);
+            if (st != MRGS_OK) return st;
+            MRGS_LAUNCH_OK("sort_pairs", stream, debug);
+
+            launch_identify_tile_ranges(R, keys, ranges, stream);
+            MRGS_LAUNCH_OK("identify_tile_ranges", stream, debug);
+
+            rp.point_list = vals;
+        }
+        rp.rec = pp.rec;
+        rp.cf = pp.cf;
+    }
+    a->num_rendered = R;
+
+    int st = launch_render_fwd(rp, stream);
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("render_fwd", stream, debug);
+    return MRGS_OK;
+}
+
+int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (a == nullptr) {
+        set_error("mrgs_backward: null args");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->P <= 0) return MRGS_OK;
+    if (a->S < 0 || a->S > MRGS_MAX_FEATURES) {
+        set_error("mrgs_backward: S=%d feature channels, supported range is 0..%d", a->S,
+                  MRGS_MAX_FEATURES);
+        return MRGS_ERR_UNSUPPORTED;
+    }
+    const bool debug = a->debug != 0;
+    const int W = a->width, H = a->height;
+    const int grid_x = (W + kTileX - 1) / kTileX, grid_y = (H + kTileY - 1) / kTileY;
+
+    MrgsGeomLayout gl;
+    MrgsImageLayout il;
+    MrgsBinningLayout bl;
+    if (mrgs_geom_layout(a->P, a->S, &gl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+    if (mrgs_image_layout(W, H, &il) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+    if (mrgs_binning_layout(a->num_rendered, &bl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
+    const size_t arena_bytes = mrgs_grad_arena_bytes(a->P, a->S);
+    if (a->grad_arena == nullptr || a->grad_arena_bytes < arena_bytes) {
+        set_error("mrgs_backward: gradient arena too small (%zu < %zu)", a->grad_arena_bytes,
+                  arena_bytes);
+        return MRGS_ERR_WORKSPACE;
+    }
+    const char* geom = (const char*)a->geom_buffer;
+    const char* img = (const char*)a->image_buffer;
+    const char* bin = (const char*)a->binning_buffer;
+    if (geom == nullptr || img == nullptr || (a->num_rendered > 0 && bin == nullptr)) {
+        set_error("mrgs_backward: missing forward buffers");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+
+    MRGS_CUDA_OK(cudaMemsetAsync(a->grad_arena, 0, arena_bytes, stream));
+
+    if (a->num_rendered > 0) {
+        RenderBwdParams rp{};
+        rp.S = a->S; rp.W = W; rp.H = H; rp.grid_x = grid_x; rp.grid_y = grid_y;
+        rp.cf_stride = gl.cf_stride; rp.grad_stride = grad_stride(a->S);
+        rp.ranges = (const uint2*)(img + il.ranges);
+        rp.point_list = (const uint32_t*)(bin + bl.point_list);
+        rp.rec = (const float*)(geom + gl.rec);
+        rp.cf = (const float*)(geom + gl.cf);
+        rp.background = a->background;
+        rp.state = (const float*)(img + il.state);
+        rp.dL_dcolor = a->dL_dout_color;
+        rp.dL_dfeature = a->dL_dout_feature;
+        rp.dL_dothers = a->dL_dout_others;
+        rp.grad_arena = (float*)a->grad_arena;
+        int st = launch_render_bwd(rp, stream);
+        if (st != MRGS_OK) return st;
+        MRGS_LAUNCH_OK("render_bwd", stream, debug);
+    }
+
+    // the reference rebuilds W,H in the backward from focal*tan*2 in fp32 (backward.cu:646-647,
+    // rasterizer_impl.cu:398-399); the truncation can give size-1 and is part of the contract
+    const float focal_y = H / (2.0f * a->tan_fovy);
+    const float focal_x = W / (2.0f * a->tan_fovx);
+    volatile float fw = focal_x * a->tan_fovx;
+    volatile float fh = focal_y * a->tan_fovy;
+    const int Wb = (int)(fw * 2.0f);
+    const int Hb = (int)(fh * 2.0f);
+
+    PreprocessBwdParams pb{};
+    pb.P = a->P; pb.S = a->S; pb.D = a->sh_degree; pb.M = a->sh_coeffs; pb.W = Wb; pb.H = Hb;
+    pb.cf_stride = gl.cf_stride; pb.grad_stride = grad_stride(a->S);
+    pb.means3D = a->means3D; pb.scales = a->scales; pb.rotations = a->rotations; pb.shs = a->shs;
+    pb.transMat_precomp = a->transMat_precomp;
+    pb.viewmatrix = a->viewmatrix; pb.projmatrix = a->projmatrix; pb.campos = a->campos;
+    pb.radii = a->radii;
+    pb.rec = (const float*)(geom + gl.rec);
+    pb.clamped = (const uint8_t*)(geom + gl.clamped);
+    pb.grad_arena = (const float*)a->grad_arena;
+    pb.dL_dmeans2D = a->dL_dmeans2D; pb.dL_dcolors = a->dL_dcolors; pb.dL_dfeatures = a->dL_dfeatures;
+    pb.dL_dopacity = a->dL_dopacity; pb.dL_dmeans3D = a->dL_dmeans3D; pb.dL_dtransMat = a->dL_dtransMat;
+    pb.dL_dsh = a->dL_dsh; pb.dL_dscales = a->dL_dscales; pb.dL_drotations = a->dL_drotations;
+    launch_preprocess_bwd(pb, stream);
+    MRGS_LAUNCH_OK("preprocess_bwd", stream, debug);
+    return MRGS_OK;
+}
+
+}  // extern "C"

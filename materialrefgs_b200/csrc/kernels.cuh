@@ -1,0 +1,108 @@
+// kernels.cuh — parameter blocks and launchers of the individual pipeline stages.
+#pragma once
+#include "common.cuh"
+
+namespace mrgs {
+
+struct PreprocessParams {
+    int P, S, D, M, W, H;
+    int grid_x, grid_y;
+    int cf_stride;
+    float scale_modifier;
+    int prefiltered;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* opacities;
+    const float* shs;
+    const float* colors_precomp;
+    const float* features;
+    const float* transMat_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    // outputs
+    int* radii;
+    float* rec;
+    float* cf;
+    uint8_t* clamped;
+    uint32_t* tiles_touched;
+    uint2* rect;
+};
+
+void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
+void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
+                         cudaStream_t stream);
+
+// ---- binning -------------------------------------------------------------------------------
+size_t scan_temp_bytes(int P);
+size_t sort_temp_bytes(int64_t R);
+int run_inclusive_scan(const uint32_t* in, uint32_t* out, int P, void* temp, size_t temp_bytes,
+                       cudaStream_t stream);
+void launch_duplicate_with_keys(int P, const float* rec, const uint2* rect, const int* radii,
+                                const uint32_t* offsets, uint64_t* keys, uint32_t* values,
+                                int grid_x, cudaStream_t stream);
+int run_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
+                   uint32_t* vals_out, int R, int end_bit, void* temp, size_t temp_bytes,
+                   cudaStream_t stream);
+void launch_identify_tile_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+uint32_t higher_msb(uint32_t n);
+
+// ---- tile blend ----------------------------------------------------------------------------
+struct RenderFwdParams {
+    int S, W, H, grid_x, grid_y, cf_stride;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float* rec;
+    const float* cf;
+    const float* background;
+    float* state;  // [tiles][5][256]
+    float* out_color;
+    float* out_feature;
+    float* out_others;
+};
+int launch_render_fwd(const RenderFwdParams& p, cudaStream_t stream);
+
+struct RenderBwdParams {
+    int S, W, H, grid_x, grid_y, cf_stride, grad_stride;
+    const uint2* ranges;
+    const uint32_t* point_list;
+    const float* rec;
+    const float* cf;
+    const float* background;
+    const float* state;
+    const float* dL_dcolor;
+    const float* dL_dfeature;
+    const float* dL_dothers;
+    float* grad_arena;  // [P][grad_stride], zero-initialised
+};
+int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
+
+struct PreprocessBwdParams {
+    int P, S, D, M, W, H;  // W,H here are the reference's recomputed int(focal*tan*2) values
+    int cf_stride, grad_stride;
+    const float* means3D;
+    const float* scales;
+    const float* rotations;
+    const float* shs;
+    const float* transMat_precomp;
+    const float* viewmatrix;
+    const float* projmatrix;
+    const float* campos;
+    const int* radii;
+    const float* rec;
+    const uint8_t* clamped;
+    const float* grad_arena;
+    float* dL_dmeans2D;
+    float* dL_dcolors;
+    float* dL_dfeatures;
+    float* dL_dopacity;
+    float* dL_dmeans3D;
+    float* dL_dtransMat;
+    float* dL_dsh;
+    float* dL_dscales;
+    float* dL_drotations;
+};
+void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
+
+}  // namespace mrgs

@@ -1,0 +1,278 @@
+"""Host-side mirror of the reference rasterizer API, backed by libmrgs.so.
+
+Same names, argument meaning, return tuple and error behaviour as
+submodules/diff-surfel-rasterization/diff_surfel_rasterization/__init__.py:
+  GaussianRasterizationSettings (:167-179), GaussianRasterizer (:181-235),
+  _RasterizeGaussians.forward/backward (:47-165), rasterize_gaussians (:22-45).
+Differences that a caller cannot observe: kernels run on the CURRENT torch stream (the
+reference uses the legacy default stream), scratch buffers have this library's own layout,
+and S > 24 raises instead of silently overflowing MAX_FEATURES.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+def _ptr(t: torch.Tensor | None) -> int | None:
+    if t is None or t.numel() == 0:
+        return None
+    return t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.numel() == 0:
+        return t
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be float32")
+    return t.contiguous()
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+class ForwardState(NamedTuple):
+    """What the forward keeps for the backward (the reference's geomBuffer / binningBuffer /
+    imgBuffer triple, rast/rasterize_points.cu:96-101)."""
+    num_rendered: int
+    geom: torch.Tensor
+    binning: torch.Tensor
+    image: torch.Tensor
+
+
+def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scales, rotations,
+                          scale_modifier, transMat_precomp, viewmatrix, projmatrix, tanfovx,
+                          tanfovy, image_height, image_width, sh, sh_degree, campos, prefiltered,
+                          debug):
+    """Equivalent of _C.rasterize_gaussians (rast/rasterize_points.cu:41-144): returns
+    (num_rendered, contrib, color, feature, others, radii, geomBuffer, binningBuffer, imgBuffer)."""
+    lib = _lib.load()
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise RuntimeError("means3D must have dimensions (num_points, 3)")
+    dev = means3D.device
+    P = means3D.shape[0]
+    if features.dim() != 2:
+        raise RuntimeError("features must have dimensions (num_points, S)")
+    S = features.shape[1]
+    if S > _lib.MAX_FEATURES:
+        raise RuntimeError(f"features has {S} channels; at most {_lib.MAX_FEATURES} are supported")
+    H, W = int(image_height), int(image_width)
+
+    bg = _f32c(bg, "background"); means3D = _f32c(means3D, "means3D")
+    colors_precomp = _f32c(colors_precomp, "colors"); opacities = _f32c(opacities, "opacity")
+    scales = _f32c(scales, "scales"); rotations = _f32c(rotations, "rotations")
+    transMat_precomp = _f32c(transMat_precomp, "transMat_precomp")
+    viewmatrix = _f32c(viewmatrix, "viewmatrix"); projmatrix = _f32c(projmatrix, "projmatrix")
+    sh = _f32c(sh, "sh"); campos = _f32c(campos, "campos")
+    if features.numel() != 0:
+        features = _f32c(features, "features")
+
+    i32 = dict(dtype=torch.int32, device=dev)
+    f32 = dict(dtype=torch.float32, device=dev)
+    contrib = torch.zeros((1, H, W), **i32)  # dead output in the reference as well (always 0)
+    if P == 0:
+        z = lambda c: torch.zeros((c, H, W), **f32)
+        e = torch.empty(0, dtype=torch.uint8, device=dev)
+        return 0, contrib, z(3), z(S), z(7), torch.zeros((0,), **i32), e, e.clone(), e.clone()
+
+    color = torch.empty((3, H, W), **f32)
+    feature = torch.empty((S, H, W), **f32)
+    others = torch.empty((7, H, W), **f32)
+    radii = torch.empty((P,), **i32)
+    geom = torch.empty(lib.mrgs_geom_bytes(P, S), dtype=torch.uint8, device=dev)
+    image = torch.empty(lib.mrgs_image_bytes(W, H), dtype=torch.uint8, device=dev)
+
+    holder = {}
+
+    def _alloc(_ctx, nbytes):
+        t = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        holder["t"] = t
+        return t.data_ptr()
+
+    M = sh.shape[1] if sh.numel() != 0 else 0
+    a = _lib.ForwardArgs()
+    a.P, a.S, a.sh_degree, a.sh_coeffs, a.width, a.height = P, S, int(sh_degree), int(M), W, H
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
+    a.prefiltered, a.debug = int(bool(prefiltered)), int(bool(debug))
+    a.background, a.means3D, a.shs = _ptr(bg), _ptr(means3D), _ptr(sh)
+    a.colors_precomp, a.features, a.opacities = _ptr(colors_precomp), _ptr(features), _ptr(opacities)
+    a.scales, a.rotations, a.transMat_precomp = _ptr(scales), _ptr(rotations), _ptr(transMat_precomp)
+    a.viewmatrix, a.projmatrix, a.campos = _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos)
+    a.out_color, a.out_feature, a.out_others, a.radii = _ptr(color), _ptr(feature), _ptr(others), _ptr(radii)
+    a.geom_buffer, a.geom_bytes = geom.data_ptr(), geom.numel()
+    a.image_buffer, a.image_bytes = image.data_ptr(), image.numel()
+    cb = _lib.alloc_fn(_alloc)
+    a.binning_alloc, a.binning_ctx = cb, None
+
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mrgs_forward(C.byref(a), C.c_void_p(stream)), "mrgs_forward")
+    binning = holder.get("t")
+    if binning is None:
+        binning = torch.empty(0, dtype=torch.uint8, device=dev)
+    return int(a.num_rendered), contrib, color, feature, others, radii, geom, binning, image
+
+
+def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales, rotations,
+                           scale_modifier, transMat_precomp, viewmatrix, projmatrix, tanfovx,
+                           tanfovy, dL_dout_color, dL_dout_feature, dL_dout_others, sh, sh_degree,
+                           campos, geom, num_rendered, binning, image, contrib, debug):
+    """Equivalent of _C.rasterize_gaussians_backward (rast/rasterize_points.cu:146-252): returns
+    (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
+    dL_dscales, dL_drotations)."""
+    lib = _lib.load()
+    dev = means3D.device
+    P = means3D.shape[0]
+    S = features.shape[1]
+    H, W = dL_dout_color.shape[1], dL_dout_color.shape[2]
+    M = sh.shape[1] if sh.numel() != 0 else 0
+    f32 = dict(dtype=torch.float32, device=dev)
+
+    out_shapes = [(P, 3), (P, 3), (P, S), (P, 1), (P, 3), (P, 9), (P, M, 3), (P, 2), (P, 4)]
+    if P == 0:
+        return tuple(torch.zeros(s, **f32) for s in out_shapes)
+    (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
+     dL_dscales, dL_drotations) = (torch.empty(s, **f32) for s in out_shapes)
+    has_sr = scales.numel() != 0
+    if not has_sr:  # never written for precomputed transforms; the reference returns zeros
+        dL_dscales.zero_(); dL_drotations.zero_()
+    if M == 0:
+        pass  # dL_dsh is (P,0,3)
+
+    arena = torch.empty(lib.mrgs_grad_arena_bytes(P, S), dtype=torch.uint8, device=dev)
+
+    a = _lib.BackwardArgs()
+    a.P, a.S, a.sh_degree, a.sh_coeffs, a.width, a.height = P, S, int(sh_degree), int(M), W, H
+    a.tan_fovx, a.tan_fovy, a.scale_modifier = float(tanfovx), float(tanfovy), float(scale_modifier)
+    a.debug, a.num_rendered = int(bool(debug)), int(num_rendered)
+    keep = [_f32c(t, n) for t, n in (
+        (bg, "background"), (means3D, "means3D"), (sh, "sh"), (colors_precomp, "colors"),
+        (features, "features") if features.numel() else (features, "features"),
+        (scales, "scales"), (rotations, "rotations"), (transMat_precomp, "transMat_precomp"),
+        (viewmatrix, "viewmatrix"), (projmatrix, "projmatrix"), (campos, "campos"),
+        (dL_dout_color, "dL_dout_color"), (dL_dout_feature, "dL_dout_feature"),
+        (dL_dout_others, "dL_dout_others"))]
+    (bg_, means_, sh_, col_, feat_, sc_, rot_, tm_, vm_, pm_, cam_, gc_, gf_, go_) = keep
+    a.background, a.means3D, a.shs, a.colors_precomp = _ptr(bg_), _ptr(means_), _ptr(sh_), _ptr(col_)
+    a.features, a.scales, a.rotations, a.transMat_precomp = _ptr(feat_), _ptr(sc_), _ptr(rot_), _ptr(tm_)
+    a.viewmatrix, a.projmatrix, a.campos = _ptr(vm_), _ptr(pm_), _ptr(cam_)
+    a.radii = _ptr(radii.contiguous())
+    a.geom_buffer, a.binning_buffer, a.image_buffer = _ptr(geom), _ptr(binning), _ptr(image)
+    a.dL_dout_color, a.dL_dout_feature, a.dL_dout_others = _ptr(gc_), _ptr(gf_), _ptr(go_)
+    a.dL_dmeans2D, a.dL_dcolors, a.dL_dfeatures = _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dfeatures)
+    a.dL_dopacity, a.dL_dmeans3D, a.dL_dtransMat = _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dtransMat)
+    a.dL_dsh = _ptr(dL_dsh)
+    a.dL_dscales = _ptr(dL_dscales) if has_sr else None
+    a.dL_drotations = _ptr(dL_drotations) if has_sr else None
+    a.grad_arena, a.grad_arena_bytes = arena.data_ptr(), arena.numel()
+
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.mrgs_backward(C.byref(a), C.c_void_p(stream)), "mrgs_backward")
+    return (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
+            dL_dscales, dL_drotations)
+
+
+def mark_visible_raw(positions, viewmatrix, projmatrix):
+    lib = _lib.load()
+    P = positions.shape[0]
+    present = torch.zeros((P,), dtype=torch.bool, device=positions.device)
+    if P != 0:
+        pos = _f32c(positions, "means3D"); vm = _f32c(viewmatrix, "viewmatrix"); pm = _f32c(projmatrix, "projmatrix")
+        with torch.cuda.device(positions.device):
+            stream = torch.cuda.current_stream(positions.device).cuda_stream
+            _lib.check(lib.mrgs_mark_visible(P, pos.data_ptr(), vm.data_ptr(), pm.data_ptr(),
+                                             present.data_ptr(), C.c_void_p(stream)), "mrgs_mark_visible")
+    return present
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
+                        cov3Ds_precomp, raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, features, opacities,
+                                     scales, rotations, cov3Ds_precomp, raster_settings)
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
+                cov3Ds_precomp, raster_settings):
+        rs = raster_settings
+        (num_rendered, contrib, color, feature, depth, radii, geom, binning, image) = rasterize_forward_raw(
+            rs.bg, means3D, colors_precomp, features, opacities, scales, rotations, rs.scale_modifier,
+            cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+            rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        ctx.raster_settings = rs
+        ctx.num_rendered = num_rendered
+        ctx.save_for_backward(colors_precomp, features, means3D, scales, rotations, cov3Ds_precomp,
+                              radii, sh, geom, binning, image, contrib)
+        ctx.mark_non_differentiable(contrib, radii)
+        return contrib, color, feature, radii, depth
+
+    @staticmethod
+    def backward(ctx, grad_out_contrib, grad_out_color, grad_out_feature, grad_radii, grad_depth):
+        rs = ctx.raster_settings
+        (colors_precomp, features, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom,
+         binning, image, contrib) = ctx.saved_tensors
+        (grad_means2D, grad_colors_precomp, grad_features, grad_opacities, grad_means3D,
+         grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations) = rasterize_backward_raw(
+            rs.bg, means3D, radii, colors_precomp, features, scales, rotations, rs.scale_modifier,
+            cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color,
+            grad_out_feature, grad_depth, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered,
+            binning, image, contrib, rs.debug)
+        # one gradient per forward input (the reference returns a surplus trailing None)
+        return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_features,
+                grad_opacities, grad_scales, grad_rotations, grad_cov3Ds_precomp, None)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            return mark_visible_raw(positions, rs.viewmatrix, rs.projmatrix)
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, features=None,
+                scales=None, rotations=None, cov3D_precomp=None):
+        rs = self.raster_settings
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        empty = lambda: torch.empty(0, dtype=torch.float32, device=means3D.device)
+        if shs is None:
+            shs = empty()
+        if colors_precomp is None:
+            colors_precomp = empty()
+        if features is None:
+            features = torch.empty_like(means3D[..., :0])
+        if scales is None:
+            scales = empty()
+        if rotations is None:
+            rotations = empty()
+        if cov3D_precomp is None:
+            cov3D_precomp = empty()
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales,
+                                   rotations, cov3D_precomp, rs)
