@@ -192,6 +192,28 @@ MRGS_API size_t mrgs_grad_arena_bytes(int32_t P, int32_t S);
 /* floats per surfel in the raw gradient arena and the field offsets inside one row */
 MRGS_API int32_t mrgs_grad_arena_stride(int32_t S);
 
+/* Optional per-stage timing: when enabled, every entry point brackets each pipeline stage with
+ * CUDA events on the launching stream. mrgs_profile_read() waits for the pending events and
+ * returns accumulated milliseconds and call counts per stage since the last reset; it returns the
+ * number of stages. mrgs_launch_count() = kernels of THIS library launched since the last reset
+ * (CUB launches inside the scan / sort stages are not counted). */
+#define MRGS_STAGE_PREPROCESS_FWD 0
+#define MRGS_STAGE_SCAN 1
+#define MRGS_STAGE_DUPLICATE 2
+#define MRGS_STAGE_SORT 3
+#define MRGS_STAGE_RANGES 4
+#define MRGS_STAGE_RENDER_FWD 5
+#define MRGS_STAGE_RENDER_BWD 6
+#define MRGS_STAGE_PREPROCESS_BWD 7
+#define MRGS_STAGE_SHADE_FWD 8
+#define MRGS_STAGE_SHADE_BWD 9
+#define MRGS_STAGE_CUBEMAP 10
+#define MRGS_STAGE_COUNT 11
+MRGS_API void mrgs_profile_enable(int32_t on);
+MRGS_API void mrgs_profile_reset(void);
+MRGS_API int mrgs_profile_read(double* ms, int64_t* calls, int32_t n);
+MRGS_API int64_t mrgs_launch_count(void);
+
 MRGS_API int mrgs_forward(MrgsForwardArgs* args, void* stream);
 MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
 MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

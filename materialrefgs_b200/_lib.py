@@ -86,6 +86,10 @@ SYMBOLS = {
     "mrgs_tile_slot": (C.c_int, [C.c_int32, C.c_int32]),
     "mrgs_grad_arena_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "mrgs_grad_arena_stride": (C.c_int32, [C.c_int32]),
+    "mrgs_profile_enable": (None, [C.c_int32]),
+    "mrgs_profile_reset": (None, []),
+    "mrgs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
+    "mrgs_launch_count": (C.c_int64, []),
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
@@ -122,6 +126,19 @@ def load() -> C.CDLL:
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+STAGES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "render_fwd", "render_bwd",
+          "preprocess_bwd", "shade_fwd", "shade_bwd", "cubemap")
+
+
+def profile_read() -> dict:
+    """{stage: (total_ms, calls)} since the last mrgs_profile_reset()."""
+    n = len(STAGES)
+    ms = (C.c_double * n)()
+    calls = (C.c_int64 * n)()
+    load().mrgs_profile_read(ms, calls, n)
+    return {s: (ms[i], calls[i]) for i, s in enumerate(STAGES)}
 
 
 def last_error() -> str:

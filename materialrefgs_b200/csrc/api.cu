@@ -37,6 +37,54 @@ static int32_t* pinned_slot() {
     return slot;
 }
 
+// ---- optional per-stage timing (CUDA events on the launching stream) + own-kernel launch count
+struct Profiler {
+    bool enabled = false;
+    cudaEvent_t ev[MRGS_STAGE_COUNT][2];
+    bool created = false;
+    bool pending[MRGS_STAGE_COUNT] = {};
+    double ms[MRGS_STAGE_COUNT] = {};
+    long long calls[MRGS_STAGE_COUNT] = {};
+    long long launches = 0;
+};
+static Profiler g_prof;
+
+static void prof_collect() {
+    for (int s = 0; s < MRGS_STAGE_COUNT; ++s) {
+        if (!g_prof.pending[s]) continue;
+        float t = 0.f;
+        if (cudaEventSynchronize(g_prof.ev[s][1]) == cudaSuccess &&
+            cudaEventElapsedTime(&t, g_prof.ev[s][0], g_prof.ev[s][1]) == cudaSuccess) {
+            g_prof.ms[s] += t;
+            g_prof.calls[s] += 1;
+        }
+        g_prof.pending[s] = false;
+    }
+}
+
+struct StageScope {
+    int stage;
+    cudaStream_t stream;
+    StageScope(int s, cudaStream_t st, int own_launches) : stage(s), stream(st) {
+        g_prof.launches += own_launches;
+        if (!g_prof.enabled) return;
+        if (!g_prof.created) {
+            for (int i = 0; i < MRGS_STAGE_COUNT; ++i) {
+                cudaEventCreate(&g_prof.ev[i][0]);
+                cudaEventCreate(&g_prof.ev[i][1]);
+            }
+            g_prof.created = true;
+        }
+        if (g_prof.pending[stage]) prof_collect();  // one in-flight measurement per stage
+        cudaEventRecord(g_prof.ev[stage][0], stream);
+    }
+    ~StageScope() {
+        if (!g_prof.enabled) return;
+        cudaEventRecord(g_prof.ev[stage][1], stream);
+        g_prof.pending[stage] = true;
+    }
+};
+
 }  // namespace mrgs
 
 using namespace mrgs;
@@ -50,6 +98,25 @@ int32_t mrgs_grad_arena_stride(int32_t S) { return grad_stride(S); }
 size_t mrgs_grad_arena_bytes(int32_t P, int32_t S) {
     return align_up((size_t)P * grad_stride(S) * sizeof(float));
 }
+
+void mrgs_profile_enable(int32_t on) { g_prof.enabled = on != 0; }
+void mrgs_profile_reset(void) {
+    prof_collect();
+    for (int s = 0; s < MRGS_STAGE_COUNT; ++s) {
+        g_prof.ms[s] = 0.0;
+        g_prof.calls[s] = 0;
+    }
+    g_prof.launches = 0;
+}
+int mrgs_profile_read(double* ms, int64_t* calls, int32_t n) {
+    prof_collect();
+    for (int s = 0; s < n && s < MRGS_STAGE_COUNT; ++s) {
+        if (ms) ms[s] = g_prof.ms[s];
+        if (calls) calls[s] = g_prof.calls[s];
+    }
+    return MRGS_STAGE_COUNT;
+}
+int64_t mrgs_launch_count(void) { return g_prof.launches; }
 
 int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out) {
     if (out == nullptr || P < 0 || S < 0 || S > MRGS_MAX_FEATURES) {
@@ -221,11 +288,18 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         pp.rect = (uint2*)(geom + gl.rect);
         uint32_t* offsets = (uint32_t*)(geom + gl.point_offsets);
 
-        launch_preprocess_fwd(pp, stream);
+        {
+            StageScope sc(MRGS_STAGE_PREPROCESS_FWD, stream, 1);
+            launch_preprocess_fwd(pp, stream);
+        }
         MRGS_LAUNCH_OK("preprocess_fwd", stream, debug);
 
-        int st = run_inclusive_scan(pp.tiles_touched, offsets, a->P, geom + gl.scan_temp,
+        int st;
+        {
+            StageScope sc(MRGS_STAGE_SCAN, stream, 0);
+            st = run_inclusive_scan(pp.tiles_touched, offsets, a->P, geom + gl.scan_temp,
                                     gl.scan_temp_bytes, stream);
+        }
         if (st != MRGS_OK) return st;
         MRGS_LAUNCH_OK("scan", stream, debug);
 
@@ -263,17 +337,26 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
             uint32_t* vals_unsorted = (uint32_t*)(bin + bl.point_list_unsorted);
             uint32_t* vals = (uint32_t*)(bin + bl.point_list);
 
-            launch_duplicate_with_keys(a->P, pp.rec, pp.rect, a->radii, offsets, keys_unsorted,
-                                       vals_unsorted, grid_x, stream);
+            {
+                StageScope sc(MRGS_STAGE_DUPLICATE, stream, 1);
+                launch_duplicate_with_keys(a->P, pp.rec, pp.rect, a->radii, offsets, keys_unsorted,
+                                           vals_unsorted, grid_x, stream);
+            }
             MRGS_LAUNCH_OK("duplicate_with_keys", stream, debug);
 
             const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);
-            st = run_sort_pairs(keys_unsorted, keys, vals_unsorted, vals, R, end_bit,
-                                bin + bl.sort_temp, bl.sort_temp_bytes, stream);
+            {
+                StageScope sc(MRGS_STAGE_SORT, stream, 0);
+                st = run_sort_pairs(keys_unsorted, keys, vals_unsorted, vals, R, end_bit,
+                                    bin + bl.sort_temp, bl.sort_temp_bytes, stream);
+            }
             if (st != MRGS_OK) return st;
             MRGS_LAUNCH_OK("sort_pairs", stream, debug);
 
-            launch_identify_tile_ranges(R, keys, ranges, stream);
+            {
+                StageScope sc(MRGS_STAGE_RANGES, stream, 1);
+                launch_identify_tile_ranges(R, keys, ranges, stream);
+            }
             MRGS_LAUNCH_OK("identify_tile_ranges", stream, debug);
 
             rp.point_list = vals;
@@ -283,7 +366,11 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
     }
     a->num_rendered = R;
 
-    int st = launch_render_fwd(rp, stream);
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_RENDER_FWD, stream, 1);
+        st = launch_render_fwd(rp, stream);
+    }
     if (st != MRGS_OK) return st;
     MRGS_LAUNCH_OK("render_fwd", stream, debug);
     return MRGS_OK;
@@ -341,7 +428,11 @@ int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
         rp.dL_dfeature = a->dL_dout_feature;
         rp.dL_dothers = a->dL_dout_others;
         rp.grad_arena = (float*)a->grad_arena;
-        int st = launch_render_bwd(rp, stream);
+        int st;
+        {
+            StageScope sc(MRGS_STAGE_RENDER_BWD, stream, 1);
+            st = launch_render_bwd(rp, stream);
+        }
         if (st != MRGS_OK) return st;
         MRGS_LAUNCH_OK("render_bwd", stream, debug);
     }
@@ -368,7 +459,10 @@ int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
     pb.dL_dmeans2D = a->dL_dmeans2D; pb.dL_dcolors = a->dL_dcolors; pb.dL_dfeatures = a->dL_dfeatures;
     pb.dL_dopacity = a->dL_dopacity; pb.dL_dmeans3D = a->dL_dmeans3D; pb.dL_dtransMat = a->dL_dtransMat;
     pb.dL_dsh = a->dL_dsh; pb.dL_dscales = a->dL_dscales; pb.dL_drotations = a->dL_drotations;
-    launch_preprocess_bwd(pb, stream);
+    {
+        StageScope sc(MRGS_STAGE_PREPROCESS_BWD, stream, 1);
+        launch_preprocess_bwd(pb, stream);
+    }
     MRGS_LAUNCH_OK("preprocess_bwd", stream, debug);
     return MRGS_OK;
 }

@@ -52,6 +52,8 @@ def _run(mod, cloud, cam, bg, grads, sh_degree=3, scale_modifier=1.0, use_sh=Tru
 
 
 def _rel_err(a, b):
+    if b.numel() == 0:
+        return 0.0
     denom = b.abs().max().clamp_min(1e-20)
     return ((a - b).abs().max() / denom).item()
 
@@ -113,7 +115,13 @@ def test_forward_buffers_bit_exact(ref_ext, P, S, W, H, opacity):
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     assert torch.equal(im["ranges"], ir["ranges"][:tiles])
     assert torch.equal(im["n_contrib"], ir["n_contrib"][0])
-    assert torch.equal(im["median_contrib"], ir["n_contrib"][1])
+    # The reference stores (uint32)(-1.0f) for pixels of EMPTY tiles: undefined behaviour that the
+    # compiler folds to an uninitialised register, so the median index is compared on tiles with a
+    # non-empty range only (the value is never read for pixels without contributors).
+    gx = (W + 15) // 16
+    lens = (im["ranges"][:, 1] - im["ranges"][:, 0]).view(-1, gx)
+    live = (lens > 0).repeat_interleave(16, 0).repeat_interleave(16, 1)[:H, :W]
+    assert torch.equal(im["median_contrib"][live], ir["n_contrib"][1][live])
     assert torch.equal(im["final_T"].view(torch.int32), ir["accum_alpha"][0].view(torch.int32))
     assert torch.allclose(im["M1"], ir["accum_alpha"][1], atol=1e-5, rtol=0)
     assert torch.allclose(im["M2"], ir["accum_alpha"][2], atol=1e-5, rtol=0)
