@@ -214,6 +214,85 @@ MRGS_API void mrgs_profile_reset(void);
 MRGS_API int mrgs_profile_read(double* ms, int64_t* calls, int32_t n);
 MRGS_API int64_t mrgs_launch_count(void);
 
+/* ---- fused deferred split-sum shading ---------------------------------------------------------
+ * One launch replaces get_specular_color_surfel (utils/refl_utils.py:364-419: camera rays, reflection,
+ * FG-LUT fetch, EnvLight mip query, specular weight) and the compositing of render_surfel
+ * (gaussian_renderer/__init__.py:372-376, :419-420, :433-445: normal to world space, /alpha,
+ * (1-refl)*base + specular, optional sRGB, + bg*(1-alpha)).
+ *   features planes: 0 refl strength, 1 roughness, 2-4 albedo (more planes may follow, ignored)
+ *   allmap planes:   1 alpha, 2-4 view-space normal (auxiliary.h:25-29)
+ *   levels[l]:       prefiltered cubemap level l, float [6][res>>l][res>>l][3] in LOGIT space
+ *                    (the fetch is followed by a sigmoid, scene/light.py:129)
+ *   lut:             float [256][256][2] split-sum DFG table (assets/bsdf_256_256.bin)
+ *   ray_matrix:      row-major 3x3 M with ray_dir = normalize(M * (x, y, 1)) for integer pixel (x,y)
+ *   normal_matrix:   row-major 3x3 Q with n_world = Q * n_view  (world_view_transform[:3,:3])
+ * Texture semantics follow nvdiffrast's dr.texture (linear clamp for the LUT, seamless
+ * linear-mipmap-linear cube fetch with mip level = per-pixel bias). */
+#define MRGS_MAX_MIP_LEVELS 12
+typedef struct MrgsShadeArgs {
+    int32_t width, height;
+    int32_t num_levels;            /* L                                                    */
+    int32_t base_res;              /* resolution of level 0                                */
+    int32_t srgb;                  /* apply linear_to_srgb to the final image              */
+    float min_roughness, max_roughness;
+    float ray_matrix[9];
+    float normal_matrix[9];
+    const float* background;       /* [3] device pointer                                   */
+    const float* base_color;       /* [3,H,W]                                              */
+    const float* features;         /* [>=5,H,W]                                            */
+    const float* allmap;           /* [7,H,W]                                              */
+    const float* lut;
+    const float* levels[MRGS_MAX_MIP_LEVELS];
+    /* forward outputs, each [3,H,W]; any may be NULL */
+    float* out_final;
+    float* out_specular;
+    float* out_direct;             /* direct_light                                         */
+    float* out_normal;             /* world-space rend_normal                              */
+    float* out_diffuse;            /* (1-refl)*base                                        */
+    /* backward inputs ([3,H,W], NULL = zero) */
+    const float* dL_dfinal;
+    const float* dL_dspecular;
+    const float* dL_ddiffuse;
+    const float* dL_dnormal;
+    /* backward outputs: fully written planes */
+    float* dL_dbase_color;         /* [3,H,W]                                              */
+    float* dL_dfeatures;           /* [>=5,H,W]: planes 0..4 written                       */
+    float* dL_dallmap;             /* [7,H,W]:   planes 1..4 written                       */
+    float* dL_dlevels[MRGS_MAX_MIP_LEVELS]; /* accumulated with atomics; zero them first  */
+} MrgsShadeArgs;
+
+MRGS_API int mrgs_shade_forward(const MrgsShadeArgs* args, void* stream);
+MRGS_API int mrgs_shade_backward(const MrgsShadeArgs* args, void* stream);
+
+/* EnvLight.__call__ (scene/light.py:98-129) for arbitrary directions: out[i] = sigmoid(cube fetch of
+ * dirs[i] at mip level get_mip(roughness[i])) (mode "specular"), or a plain bilinear fetch of
+ * levels[0] when roughness == NULL (modes "diffuse"/"pure_env"). n directions, out [n,3]. */
+MRGS_API int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs,
+                                 const float* roughness, float* out, void* stream);
+
+/* ---- EnvLight.build_mips on the device ----------------------------------------------------------
+ * Cubemaps are float [6][res][res][C]. Replaces cubemap_mip (scene/light_utils.py:66-80) and the
+ * renderutils_plugin ops diffuse_cubemap_fwd/bwd, specular_bounds, specular_cubemap_fwd/bwd
+ * (scene/renderutils/c_src/torch_bindings.cpp:740-890, kernels in c_src/cubemap.cu:110-354).
+ *   mip forward : out[res/2] = 2x2 average of in[res]
+ *   mip backward: din[res] = seamless bilinear cube fetch of 0.25*dout[res/2] at the fine texel
+ *                 directions (the reference's non-adjoint backward), C must be 3
+ *   bounds      : int32 [6][res][res][6][4] = (xmin,xmax,ymin,ymax) of the texels of each source face
+ *                 inside the cone dot(L,N) >= costheta_cutoff
+ *   specular fwd: out4 [6][res][res][4] = (sum w*rgb, sum w); the caller divides rgb by sum w
+ *   specular bwd: dcubemap [6][res][res][3] is zeroed and then accumulated from dout4's rgb
+ *   diffuse     : cosine-weighted convolution over the whole cube (16x16 level in the reference) */
+MRGS_API int mrgs_cubemap_mip_forward(const float* in, float* out, int32_t res_in, int32_t channels, void* stream);
+MRGS_API int mrgs_cubemap_mip_backward(const float* dout, float* din, int32_t res_out, void* stream);
+MRGS_API int mrgs_specular_bounds(int32_t res, float costheta_cutoff, int32_t* bounds, void* stream);
+MRGS_API int mrgs_specular_cubemap_forward(const float* cubemap, const int32_t* bounds, int32_t res, float roughness,
+                                           float costheta_cutoff, float* out4, void* stream);
+MRGS_API int mrgs_specular_cubemap_backward(const float* cubemap, const int32_t* bounds, int32_t res, float roughness,
+                                            float costheta_cutoff, const float* dout4, float* dcubemap, void* stream);
+MRGS_API int mrgs_diffuse_cubemap_forward(const float* cubemap, int32_t res, float* out, void* stream);
+MRGS_API int mrgs_diffuse_cubemap_backward(const float* cubemap, int32_t res, const float* dout, float* dcubemap,
+                                           void* stream);
+
 MRGS_API int mrgs_forward(MrgsForwardArgs* args, void* stream);
 MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
 MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,

@@ -73,6 +73,24 @@ class BackwardArgs(C.Structure):
     ]
 
 
+MAX_MIP_LEVELS = 12
+
+
+class ShadeArgs(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("num_levels", C.c_int32), ("base_res", C.c_int32),
+        ("srgb", C.c_int32), ("min_roughness", C.c_float), ("max_roughness", C.c_float),
+        ("ray_matrix", C.c_float * 9), ("normal_matrix", C.c_float * 9),
+        ("background", _fp), ("base_color", _fp), ("features", _fp), ("allmap", _fp), ("lut", _fp),
+        ("levels", _fp * MAX_MIP_LEVELS),
+        ("out_final", _fp), ("out_specular", _fp), ("out_direct", _fp), ("out_normal", _fp),
+        ("out_diffuse", _fp),
+        ("dL_dfinal", _fp), ("dL_dspecular", _fp), ("dL_ddiffuse", _fp), ("dL_dnormal", _fp),
+        ("dL_dbase_color", _fp), ("dL_dfeatures", _fp), ("dL_dallmap", _fp),
+        ("dL_dlevels", _fp * MAX_MIP_LEVELS),
+    ]
+
+
 # every symbol include/mrgs.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mrgs_abi_version": (C.c_int, []),
@@ -90,6 +108,16 @@ SYMBOLS = {
     "mrgs_profile_reset": (None, []),
     "mrgs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "mrgs_launch_count": (C.c_int64, []),
+    "mrgs_shade_forward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
+    "mrgs_shade_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
+    "mrgs_envlight_query": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_cubemap_mip_forward": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_void_p]),
+    "mrgs_cubemap_mip_backward": (C.c_int, [_fp, _fp, C.c_int32, C.c_void_p]),
+    "mrgs_specular_bounds": (C.c_int, [C.c_int32, C.c_float, _fp, C.c_void_p]),
+    "mrgs_specular_cubemap_forward": (C.c_int, [_fp, _fp, C.c_int32, C.c_float, C.c_float, _fp, C.c_void_p]),
+    "mrgs_specular_cubemap_backward": (C.c_int, [_fp, _fp, C.c_int32, C.c_float, C.c_float, _fp, _fp, C.c_void_p]),
+    "mrgs_diffuse_cubemap_forward": (C.c_int, [_fp, C.c_int32, _fp, C.c_void_p]),
+    "mrgs_diffuse_cubemap_backward": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_void_p]),
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),

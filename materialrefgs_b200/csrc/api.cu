@@ -376,6 +376,129 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
     return MRGS_OK;
 }
 
+int mrgs_shade_forward(const MrgsShadeArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_FWD, stream, 1);
+        st = launch_shade(a, false, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("shade_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_shade_backward(const MrgsShadeArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_BWD, stream, 1);
+        st = launch_shade(a, true, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("shade_bwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs, const float* roughness,
+                        float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n > 0 && (dirs == nullptr || out == nullptr)) {
+        set_error("mrgs_envlight_query: null dirs/out");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_FWD, stream, 1);
+        st = launch_envlight_query(chain, n, dirs, roughness, out, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("envlight_query", stream, false);
+    return MRGS_OK;
+}
+
+#define MRGS_CUBE_CHECK(cond, who)                                  \
+    if (!(cond)) {                                                  \
+        set_error("%s: bad arguments", who);                        \
+        return MRGS_ERR_INVALID_ARGUMENT;                           \
+    }
+
+int mrgs_cubemap_mip_forward(const float* in, float* out, int32_t res_in, int32_t channels, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(in && out && res_in >= 2 && (res_in % 2) == 0 && channels > 0, "mrgs_cubemap_mip_forward");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_cubemap_mip_fwd(in, out, res_in / 2, channels, stream);
+    }
+    MRGS_LAUNCH_OK("cubemap_mip_fwd", stream, false);
+    return MRGS_OK;
+}
+int mrgs_cubemap_mip_backward(const float* dout, float* din, int32_t res_out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(dout && din && res_out >= 1, "mrgs_cubemap_mip_backward");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_cubemap_mip_bwd(dout, din, res_out, stream);
+    }
+    MRGS_LAUNCH_OK("cubemap_mip_bwd", stream, false);
+    return MRGS_OK;
+}
+int mrgs_specular_bounds(int32_t res, float cutoff, int32_t* bounds, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(bounds && res >= 1, "mrgs_specular_bounds");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_specular_bounds(res, cutoff, bounds, stream);
+    }
+    MRGS_LAUNCH_OK("specular_bounds", stream, false);
+    return MRGS_OK;
+}
+int mrgs_specular_cubemap_forward(const float* cubemap, const int32_t* bounds, int32_t res, float roughness,
+                                  float cutoff, float* out4, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(cubemap && bounds && out4 && res >= 1, "mrgs_specular_cubemap_forward");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_specular_cubemap(false, res, roughness, cutoff, bounds, cubemap, out4, nullptr, nullptr, stream);
+    }
+    MRGS_LAUNCH_OK("specular_cubemap_fwd", stream, false);
+    return MRGS_OK;
+}
+int mrgs_specular_cubemap_backward(const float* cubemap, const int32_t* bounds, int32_t res, float roughness,
+                                   float cutoff, const float* dout4, float* dcubemap, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(bounds && dout4 && dcubemap && res >= 1, "mrgs_specular_cubemap_backward");
+    MRGS_CUDA_OK(cudaMemsetAsync(dcubemap, 0, (size_t)6 * res * res * 3 * sizeof(float), stream));
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_specular_cubemap(true, res, roughness, cutoff, bounds, cubemap, nullptr, dout4, dcubemap, stream);
+    }
+    MRGS_LAUNCH_OK("specular_cubemap_bwd", stream, false);
+    return MRGS_OK;
+}
+int mrgs_diffuse_cubemap_forward(const float* cubemap, int32_t res, float* out, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(cubemap && out && res >= 1, "mrgs_diffuse_cubemap_forward");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_diffuse_cubemap(false, res, cubemap, out, nullptr, nullptr, stream);
+    }
+    MRGS_LAUNCH_OK("diffuse_cubemap_fwd", stream, false);
+    return MRGS_OK;
+}
+int mrgs_diffuse_cubemap_backward(const float* cubemap, int32_t res, const float* dout, float* dcubemap,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(dout && dcubemap && res >= 1, "mrgs_diffuse_cubemap_backward");
+    MRGS_CUDA_OK(cudaMemsetAsync(dcubemap, 0, (size_t)6 * res * res * 3 * sizeof(float), stream));
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_diffuse_cubemap(true, res, cubemap, nullptr, dout, dcubemap, stream);
+    }
+    MRGS_LAUNCH_OK("diffuse_cubemap_bwd", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (a == nullptr) {

@@ -105,4 +105,19 @@ struct PreprocessBwdParams {
 };
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 
+// ---- deferred shading ------------------------------------------------------------------------
+int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream);
+int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
+                          float* out, cudaStream_t stream);
+
+// ---- cubemap prefilter (EnvLight.build_mips) ---------------------------------------------------
+void launch_cubemap_mip_fwd(const float* in, float* out, int res_out, int C, cudaStream_t stream);
+void launch_cubemap_mip_bwd(const float* dout, float* din, int res_out, cudaStream_t stream);
+void launch_specular_bounds(int N, float cutoff, int32_t* bounds, cudaStream_t stream);
+void launch_specular_cubemap(bool backward, int N, float roughness, float cutoff, const int32_t* bounds,
+                             const float* cubemap, float* out4, const float* dout4, float* dcubemap,
+                             cudaStream_t stream);
+void launch_diffuse_cubemap(bool backward, int N, const float* cubemap, float* out, const float* dout,
+                            float* dcubemap, cudaStream_t stream);
+
 }  // namespace mrgs

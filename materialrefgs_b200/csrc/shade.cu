@@ -1,0 +1,362 @@
+// shade.cu — fused deferred split-sum PBR shading of the rasterized G-buffer, forward and backward.
+//
+// One thread per pixel does what the reference spreads over ~35 eager torch kernels and two
+// nvdiffrast texture ops:
+//   normal to world space and /alpha      gaussian_renderer/__init__.py:46-48, :419-420
+//   camera ray, reflection, N.V           utils/refl_utils.py:54-73, :95-98, :367-371
+//   FG LUT bilinear-clamp fetch           utils/refl_utils.py:373-374
+//   roughness -> mip level                scene/light.py:88-96
+//   seamless trilinear cube fetch+sigmoid scene/light.py:118-129
+//   specular weight / specular / final    utils/refl_utils.py:377, :400-401; __init__.py:433-445
+// Texture semantics restate nvdiffrast's dr.texture (not vendored by the reference):
+// texel centres at (i+0.5)/size, u*size-0.5 taps, LUT taps clamped, cube taps that leave a face
+// continue on the adjacent face, the missing tap at a cube corner is the mean of the other three,
+// mip level = clamp(bias, 0, L-1) with linear blending between floor and floor+1.
+#include "cube_sample.cuh"
+#include "kernels.cuh"
+
+namespace mrgs {
+
+namespace {
+
+struct MipLevel {
+    int l0, l1;
+    float f;
+    float dlevel_drough;
+};
+
+// EnvLight.get_mip (scene/light.py:88-96) followed by dr.texture's level clamp
+__device__ __forceinline__ MipLevel rough_to_level(float r, float min_r, float max_r, int L) {
+    float lvl, dl;
+    if (r < max_r) {
+        lvl = (fminf(fmaxf(r, min_r), max_r) - min_r) / (max_r - min_r) * (float)(L - 2);
+        dl = (r >= min_r) ? (float)(L - 2) / (max_r - min_r) : 0.f;
+    } else {
+        lvl = (fminf(fmaxf(r, max_r), 1.0f) - max_r) / (1.0f - max_r) + (float)(L - 2);
+        dl = (r <= 1.0f) ? 1.0f / (1.0f - max_r) : 0.f;
+    }
+    MipLevel m;
+    const float c = fminf(fmaxf(lvl, 0.f), (float)(L - 1));
+    m.l0 = (int)floorf(c);
+    m.l1 = min(m.l0 + 1, L - 1);
+    m.f = (m.l1 == m.l0) ? 0.f : c - (float)m.l0;
+    m.dlevel_drough = (lvl < 0.f || lvl > (float)(L - 1)) ? 0.f : dl;
+    return m;
+}
+
+// bilinear fetch of the [256,256,2] LUT with clamp boundary; uv.x -> width, uv.y -> height
+struct LutFetch {
+    float fx, fy;          // the two channels
+    float dfx_du, dfx_dv, dfy_du, dfy_dv;
+};
+__device__ __forceinline__ LutFetch lut_fetch(const float* __restrict__ lut, float u, float v) {
+    constexpr int N = 256;
+    const float Uc = fminf(fmaxf(u * N - 0.5f, 0.f), (float)(N - 1));
+    const float Vc = fminf(fmaxf(v * N - 0.5f, 0.f), (float)(N - 1));
+    const bool u_in = (u * N - 0.5f) >= 0.f && (u * N - 0.5f) <= (float)(N - 1);
+    const bool v_in = (v * N - 0.5f) >= 0.f && (v * N - 0.5f) <= (float)(N - 1);
+    const int x0 = (int)floorf(Uc), y0 = (int)floorf(Vc);
+    const int x1 = min(x0 + 1, N - 1), y1 = min(y0 + 1, N - 1);
+    const float fu = Uc - (float)x0, fv = Vc - (float)y0;
+    const float2 a00 = __ldg(reinterpret_cast<const float2*>(lut) + y0 * N + x0);
+    const float2 a10 = __ldg(reinterpret_cast<const float2*>(lut) + y0 * N + x1);
+    const float2 a01 = __ldg(reinterpret_cast<const float2*>(lut) + y1 * N + x0);
+    const float2 a11 = __ldg(reinterpret_cast<const float2*>(lut) + y1 * N + x1);
+    LutFetch r;
+    const float w00 = (1.f - fu) * (1.f - fv), w10 = fu * (1.f - fv), w01 = (1.f - fu) * fv, w11 = fu * fv;
+    r.fx = w00 * a00.x + w10 * a10.x + w01 * a01.x + w11 * a11.x;
+    r.fy = w00 * a00.y + w10 * a10.y + w01 * a01.y + w11 * a11.y;
+    const float su = u_in ? (float)N : 0.f, sv = v_in ? (float)N : 0.f;
+    r.dfx_du = su * ((1.f - fv) * (a10.x - a00.x) + fv * (a11.x - a01.x));
+    r.dfy_du = su * ((1.f - fv) * (a10.y - a00.y) + fv * (a11.y - a01.y));
+    r.dfx_dv = sv * ((1.f - fu) * (a01.x - a00.x) + fu * (a11.x - a10.x));
+    r.dfy_dv = sv * ((1.f - fu) * (a01.y - a00.y) + fu * (a11.y - a10.y));
+    return r;
+}
+
+__device__ __forceinline__ float sigmoidf(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+constexpr float kSrgbEps = 1.1920929e-07f;
+__device__ __forceinline__ float linear_to_srgb(float x) {  // utils/graphics_utils.py:102-110
+    const float s0 = (323.0f / 25.0f) * x;
+    const float s1 = (211.0f * powf(fmaxf(x, kSrgbEps), 5.0f / 12.0f) - 11.0f) / 200.0f;
+    return x <= 0.0031308f ? s0 : s1;
+}
+__device__ __forceinline__ float dlinear_to_srgb(float x) {
+    if (x <= 0.0031308f) return 323.0f / 25.0f;
+    return (211.0f / 200.0f) * (5.0f / 12.0f) * powf(x, -7.0f / 12.0f);
+}
+
+struct PixelShade {
+    // inputs
+    F3 base, albedo, nv;
+    float rs, ro, A;
+    // intermediates
+    F3 nw, n, wo, r, rr, Ld, t, sw, spec, diff, fin_lin;
+    float Ac, ndv, rl;
+    LutFetch fg;
+    MipLevel mip;
+    FaceUV fuv;
+    Bilinear b0, b1;
+};
+
+template <bool GRAD>
+__device__ __forceinline__ void shade_pixel(const MrgsShadeArgs& p, int x, int y, size_t pix, size_t HW,
+                                            PixelShade& s) {
+    s.base = {p.base_color[pix], p.base_color[HW + pix], p.base_color[2 * HW + pix]};
+    s.rs = p.features[pix];
+    s.ro = p.features[HW + pix];
+    s.albedo = {p.features[2 * HW + pix], p.features[3 * HW + pix], p.features[4 * HW + pix]};
+    s.A = p.allmap[kAlphaOff * HW + pix];
+    s.nv = {p.allmap[(kNormalOff + 0) * HW + pix], p.allmap[(kNormalOff + 1) * HW + pix],
+            p.allmap[(kNormalOff + 2) * HW + pix]};
+    const float* Q = p.normal_matrix;
+    s.nw = {Q[0] * s.nv.x + Q[1] * s.nv.y + Q[2] * s.nv.z, Q[3] * s.nv.x + Q[4] * s.nv.y + Q[5] * s.nv.z,
+            Q[6] * s.nv.x + Q[7] * s.nv.y + Q[8] * s.nv.z};
+    s.Ac = fmaxf(s.A, 1e-6f);
+    s.n = (1.0f / s.Ac) * s.nw;
+    const float* M = p.ray_matrix;
+    const float fx = (float)x, fy = (float)y;
+    F3 d = {M[0] * fx + M[1] * fy + M[2], M[3] * fx + M[4] * fy + M[5], M[6] * fx + M[7] * fy + M[8]};
+    d = (1.0f / sqrtf(dot(d, d))) * d;
+    s.wo = {-d.x, -d.y, -d.z};
+    s.ndv = dot(s.n, s.wo);
+    s.r = (2.0f * s.ndv) * s.n - s.wo;
+    s.rl = fmaxf(sqrtf(dot(s.r, s.r)), 1e-20f);
+    s.rr = (1.0f / s.rl) * s.r;
+
+    s.fg = lut_fetch(p.lut, fminf(fmaxf(s.ndv, 0.f), 1.f), fminf(fmaxf(s.ro, 0.f), 1.f));
+
+    s.mip = rough_to_level(s.ro, p.min_roughness, p.max_roughness, p.num_levels);
+    s.fuv = dir_to_face(s.rr);
+    cube_bilinear<GRAD>(p.levels[s.mip.l0], p.base_res >> s.mip.l0, s.fuv.face, s.fuv.u, s.fuv.v, s.b0);
+    s.t = s.b0.val;
+    if (s.mip.l1 != s.mip.l0) {
+        cube_bilinear<GRAD>(p.levels[s.mip.l1], p.base_res >> s.mip.l1, s.fuv.face, s.fuv.u, s.fuv.v, s.b1);
+        s.t = (1.0f - s.mip.f) * s.b0.val + s.mip.f * s.b1.val;
+    }
+    s.Ld = {sigmoidf(s.t.x), sigmoidf(s.t.y), sigmoidf(s.t.z)};
+
+    const float k0 = 0.04f * (1.0f - s.rs);
+    s.sw = {(k0 + s.albedo.x * s.rs) * s.fg.fx + s.fg.fy, (k0 + s.albedo.y * s.rs) * s.fg.fx + s.fg.fy,
+            (k0 + s.albedo.z * s.rs) * s.fg.fx + s.fg.fy};
+    s.spec = {s.Ld.x * s.A * s.sw.x, s.Ld.y * s.A * s.sw.y, s.Ld.z * s.A * s.sw.z};
+    s.diff = (1.0f - s.rs) * s.base;
+    s.fin_lin = s.diff + s.spec;
+}
+
+__device__ __forceinline__ void store3(float* out, size_t pix, size_t HW, F3 v) {
+    if (out == nullptr) return;
+    out[pix] = v.x;
+    out[HW + pix] = v.y;
+    out[2 * HW + pix] = v.z;
+}
+__device__ __forceinline__ F3 load3p(const float* in, size_t pix, size_t HW) {
+    if (in == nullptr) return {0.f, 0.f, 0.f};
+    return {in[pix], in[HW + pix], in[2 * HW + pix]};
+}
+
+__global__ void __launch_bounds__(256) shade_fwd_kernel(const MrgsShadeArgs p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.width || y >= p.height) return;
+    const size_t HW = (size_t)p.width * p.height, pix = (size_t)y * p.width + x;
+    PixelShade s;
+    shade_pixel<false>(p, x, y, pix, HW, s);
+    F3 fin = s.fin_lin;
+    if (p.srgb) fin = {linear_to_srgb(fin.x), linear_to_srgb(fin.y), linear_to_srgb(fin.z)};
+    const float om = 1.0f - s.A;
+    fin = {fin.x + p.background[0] * om, fin.y + p.background[1] * om, fin.z + p.background[2] * om};
+    store3(p.out_final, pix, HW, fin);
+    store3(p.out_specular, pix, HW, s.spec);
+    store3(p.out_direct, pix, HW, s.Ld);
+    store3(p.out_normal, pix, HW, s.nw);
+    store3(p.out_diffuse, pix, HW, s.diff);
+}
+
+__device__ __forceinline__ void scatter_bilinear(float* __restrict__ grad_tex, const Bilinear& b, F3 g) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (b.idx[k] < 0 || b.w[k] == 0.f) continue;
+        float* q = grad_tex + 3 * (size_t)b.idx[k];
+        atomicAdd(q + 0, b.w[k] * g.x);
+        atomicAdd(q + 1, b.w[k] * g.y);
+        atomicAdd(q + 2, b.w[k] * g.z);
+    }
+}
+
+__global__ void __launch_bounds__(256) shade_bwd_kernel(const MrgsShadeArgs p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.width || y >= p.height) return;
+    const size_t HW = (size_t)p.width * p.height, pix = (size_t)y * p.width + x;
+    PixelShade s;
+    shade_pixel<true>(p, x, y, pix, HW, s);
+
+    const F3 g_fin = load3p(p.dL_dfinal, pix, HW);
+    const F3 g_spec_out = load3p(p.dL_dspecular, pix, HW);
+    const F3 g_diff_out = load3p(p.dL_ddiffuse, pix, HW);
+    const F3 g_nw_out = load3p(p.dL_dnormal, pix, HW);
+
+    float g_A = -(g_fin.x * p.background[0] + g_fin.y * p.background[1] + g_fin.z * p.background[2]);
+    F3 g_lin = g_fin;
+    if (p.srgb)
+        g_lin = {g_fin.x * dlinear_to_srgb(s.fin_lin.x), g_fin.y * dlinear_to_srgb(s.fin_lin.y),
+                 g_fin.z * dlinear_to_srgb(s.fin_lin.z)};
+    const F3 g_diff = g_lin + g_diff_out;
+    const F3 g_spec = g_lin + g_spec_out;
+
+    float g_rs = -dot(s.base, g_diff);
+    const F3 g_base = (1.0f - s.rs) * g_diff;
+
+    const F3 g_Ld = {g_spec.x * s.A * s.sw.x, g_spec.y * s.A * s.sw.y, g_spec.z * s.A * s.sw.z};
+    g_A += g_spec.x * s.Ld.x * s.sw.x + g_spec.y * s.Ld.y * s.sw.y + g_spec.z * s.Ld.z * s.sw.z;
+    const F3 g_sw = {g_spec.x * s.Ld.x * s.A, g_spec.y * s.Ld.y * s.A, g_spec.z * s.Ld.z * s.A};
+
+    g_rs += s.fg.fx * (g_sw.x * (s.albedo.x - 0.04f) + g_sw.y * (s.albedo.y - 0.04f) + g_sw.z * (s.albedo.z - 0.04f));
+    const F3 g_albedo = (s.rs * s.fg.fx) * g_sw;
+    const float k0 = 0.04f * (1.0f - s.rs);
+    const float g_fgx = g_sw.x * (k0 + s.albedo.x * s.rs) + g_sw.y * (k0 + s.albedo.y * s.rs) + g_sw.z * (k0 + s.albedo.z * s.rs);
+    const float g_fgy = g_sw.x + g_sw.y + g_sw.z;
+
+    // LUT -> N.V and roughness (torch.clamp passes the gradient on the closed interval)
+    float g_ndv = 0.f, g_ro = 0.f;
+    if (s.ndv >= 0.f && s.ndv <= 1.f) g_ndv = g_fgx * s.fg.dfx_du + g_fgy * s.fg.dfy_du;
+    if (s.ro >= 0.f && s.ro <= 1.f) g_ro = g_fgx * s.fg.dfx_dv + g_fgy * s.fg.dfy_dv;
+
+    // environment: sigmoid, mip blend, texels, level, face coordinates
+    const F3 g_t = {g_Ld.x * s.Ld.x * (1.0f - s.Ld.x), g_Ld.y * s.Ld.y * (1.0f - s.Ld.y),
+                    g_Ld.z * s.Ld.z * (1.0f - s.Ld.z)};
+    float g_u, g_v;
+    if (s.mip.l1 != s.mip.l0) {
+        const float f = s.mip.f;
+        if (p.dL_dlevels[s.mip.l0]) scatter_bilinear(p.dL_dlevels[s.mip.l0], s.b0, (1.0f - f) * g_t);
+        if (p.dL_dlevels[s.mip.l1]) scatter_bilinear(p.dL_dlevels[s.mip.l1], s.b1, f * g_t);
+        g_ro += dot(g_t, s.b1.val - s.b0.val) * s.mip.dlevel_drough;
+        g_u = dot(g_t, (1.0f - f) * s.b0.dval_du + f * s.b1.dval_du);
+        g_v = dot(g_t, (1.0f - f) * s.b0.dval_dv + f * s.b1.dval_dv);
+    } else {
+        if (p.dL_dlevels[s.mip.l0]) scatter_bilinear(p.dL_dlevels[s.mip.l0], s.b0, g_t);
+        g_u = dot(g_t, s.b0.dval_du);
+        g_v = dot(g_t, s.b0.dval_dv);
+    }
+    // u = su*a*m + .5, v = sv*b*m + .5, m = .5/|c|
+    float g_rr[3] = {0.f, 0.f, 0.f};
+    {
+        const float rrv[3] = {s.rr.x, s.rr.y, s.rr.z};
+        const float a = rrv[s.fuv.ia], b = rrv[s.fuv.ib], c = rrv[s.fuv.ic];
+        const float m = s.fuv.m;
+        const bool u_free = s.fuv.u > 0.f && s.fuv.u < 1.f, v_free = s.fuv.v > 0.f && s.fuv.v < 1.f;
+        const float gu = u_free ? g_u : 0.f, gv = v_free ? g_v : 0.f;
+        g_rr[s.fuv.ia] += gu * s.fuv.su * m;
+        g_rr[s.fuv.ib] += gv * s.fuv.sv * m;
+        g_rr[s.fuv.ic] += -(gu * s.fuv.su * a + gv * s.fuv.sv * b) * m / fabsf(c) * s.fuv.csign;
+    }
+    // rr = r / max(|r|, eps)
+    F3 g_r = {0.f, 0.f, 0.f};
+    {
+        const F3 grr = {g_rr[0], g_rr[1], g_rr[2]};
+        if (s.rl > 1e-20f)
+            g_r = (1.0f / s.rl) * (grr - dot(s.rr, grr) * s.rr);
+        else
+            g_r = (1.0f / s.rl) * grr;
+    }
+    // r = 2 n (n.wo) - wo ; ndv = n.wo
+    F3 g_n = (2.0f * s.ndv) * g_r;
+    g_ndv += 2.0f * dot(s.n, g_r);
+    g_n = g_n + g_ndv * s.wo;
+    // n = nw / max(A, 1e-6)
+    F3 g_nw = (1.0f / s.Ac) * g_n;
+    if (s.A >= 1e-6f) g_A += -dot(s.n, g_n) / s.Ac;
+    g_nw = g_nw + g_nw_out;
+    const float* Q = p.normal_matrix;
+    const F3 g_nv = {Q[0] * g_nw.x + Q[3] * g_nw.y + Q[6] * g_nw.z, Q[1] * g_nw.x + Q[4] * g_nw.y + Q[7] * g_nw.z,
+                     Q[2] * g_nw.x + Q[5] * g_nw.y + Q[8] * g_nw.z};
+
+    store3(p.dL_dbase_color, pix, HW, g_base);
+    if (p.dL_dfeatures) {
+        p.dL_dfeatures[pix] = g_rs;
+        p.dL_dfeatures[HW + pix] = g_ro;
+        p.dL_dfeatures[2 * HW + pix] = g_albedo.x;
+        p.dL_dfeatures[3 * HW + pix] = g_albedo.y;
+        p.dL_dfeatures[4 * HW + pix] = g_albedo.z;
+    }
+    if (p.dL_dallmap) {
+        p.dL_dallmap[kAlphaOff * HW + pix] = g_A;
+        p.dL_dallmap[(kNormalOff + 0) * HW + pix] = g_nv.x;
+        p.dL_dallmap[(kNormalOff + 1) * HW + pix] = g_nv.y;
+        p.dL_dallmap[(kNormalOff + 2) * HW + pix] = g_nv.z;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+envlight_query_kernel(const MrgsShadeArgs p, long long n, const float* __restrict__ dirs,
+                      const float* __restrict__ roughness, float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const F3 d = {dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]};
+    const FaceUV f = dir_to_face(d);
+    Bilinear b0, b1;
+    F3 t;
+    if (roughness != nullptr) {
+        const MipLevel m = rough_to_level(roughness[i], p.min_roughness, p.max_roughness, p.num_levels);
+        cube_bilinear<false>(p.levels[m.l0], p.base_res >> m.l0, f.face, f.u, f.v, b0);
+        t = b0.val;
+        if (m.l1 != m.l0) {
+            cube_bilinear<false>(p.levels[m.l1], p.base_res >> m.l1, f.face, f.u, f.v, b1);
+            t = (1.0f - m.f) * b0.val + m.f * b1.val;
+        }
+    } else {
+        cube_bilinear<false>(p.levels[0], p.base_res, f.face, f.u, f.v, b0);
+        t = b0.val;
+    }
+    out[3 * i] = sigmoidf(t.x);
+    out[3 * i + 1] = sigmoidf(t.y);
+    out[3 * i + 2] = sigmoidf(t.z);
+}
+
+int validate(const MrgsShadeArgs* a, const char* who, bool need_maps) {
+    if (a == nullptr) {
+        set_error("%s: null args", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->num_levels < 2 || a->num_levels > MRGS_MAX_MIP_LEVELS || a->base_res <= 0 ||
+        (a->base_res >> (a->num_levels - 1)) < 1) {
+        set_error("%s: bad mip chain (levels=%d, base_res=%d)", who, a->num_levels, a->base_res);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    for (int l = 0; l < a->num_levels; ++l)
+        if (a->levels[l] == nullptr) {
+            set_error("%s: level %d is null", who, l);
+            return MRGS_ERR_INVALID_ARGUMENT;
+        }
+    if (need_maps && (a->width <= 0 || a->height <= 0 || !a->base_color || !a->features || !a->allmap || !a->lut)) {
+        set_error("%s: missing G-buffer / LUT pointers or bad size %dx%d", who, a->width, a->height);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    return MRGS_OK;
+}
+
+}  // namespace
+
+int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream) {
+    int st = validate(a, backward ? "mrgs_shade_backward" : "mrgs_shade_forward", true);
+    if (st != MRGS_OK) return st;
+    const dim3 grid((a->width + 31) / 32, (a->height + 7) / 8);
+    if (backward)
+        shade_bwd_kernel<<<grid, 256, 0, stream>>>(*a);
+    else
+        shade_fwd_kernel<<<grid, 256, 0, stream>>>(*a);
+    return MRGS_OK;
+}
+
+int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
+                          float* out, cudaStream_t stream) {
+    int st = validate(a, "mrgs_envlight_query", false);
+    if (st != MRGS_OK) return st;
+    if (n <= 0) return MRGS_OK;
+    envlight_query_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(*a, n, dirs, roughness, out);
+    return MRGS_OK;
+}
+
+}  // namespace mrgs

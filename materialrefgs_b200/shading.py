@@ -1,0 +1,254 @@
+"""Host-side mirror of the reference's deferred split-sum shading, backed by the fused CUDA
+kernels of libmrgs.so (mrgs_shade_forward / mrgs_shade_backward / mrgs_envlight_query).
+
+Reference interfaces mirrored here (same names and argument meaning):
+  EnvLight                      scene/light.py:21-129 (base parameter in logit space, build_mips,
+                                get_mip, __call__(l, mode, roughness) -> sigmoid(texture fetch))
+  get_specular_color_surfel     utils/refl_utils.py:364-419 (visibility branch excluded: OptiX/mesh
+                                tracing stays on the reference)
+  shade_surfel                  the part of render_surfel after the rasterizer call,
+                                gaussian_renderer/__init__.py:372-469
+There is no torch fallback: every function raises if libmrgs.so is unavailable.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_LUT_PATH = Path(__file__).resolve().parent / "assets" / "bsdf_256_256.bin"
+_LUT_CACHE: dict = {}
+
+
+def fg_lut(device) -> torch.Tensor:
+    """The 256x256x2 split-sum DFG table (utils/refl_utils.py:9), cached per device."""
+    key = str(device)
+    if key not in _LUT_CACHE:
+        arr = np.fromfile(_LUT_PATH, dtype=np.float32).reshape(256, 256, 2)
+        _LUT_CACHE[key] = torch.from_numpy(arr).to(device).contiguous()
+    return _LUT_CACHE[key]
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _chain_args(levels, min_roughness, max_roughness) -> _lib.ShadeArgs:
+    if not 2 <= len(levels) <= _lib.MAX_MIP_LEVELS:
+        raise RuntimeError(f"mip chain must have 2..{_lib.MAX_MIP_LEVELS} levels, got {len(levels)}")
+    a = _lib.ShadeArgs()
+    a.num_levels = len(levels)
+    a.base_res = int(levels[0].shape[1])
+    a.min_roughness, a.max_roughness = float(min_roughness), float(max_roughness)
+    for i, l in enumerate(levels):
+        if not l.is_cuda or l.dtype != torch.float32 or not l.is_contiguous():
+            raise RuntimeError("mip levels must be contiguous float32 CUDA tensors")
+        if tuple(l.shape) != (6, a.base_res >> i, a.base_res >> i, 3):
+            raise RuntimeError(f"level {i} has shape {tuple(l.shape)}, expected (6,{a.base_res >> i},{a.base_res >> i},3)")
+        a.levels[i] = l.data_ptr()
+    return a
+
+
+def ray_matrix(HWK, R) -> np.ndarray:
+    """M with ray_dir ∝ M @ (x, y, 1): the pixel_camera -> world chain of sample_camera_rays
+    (utils/refl_utils.py:54-73) collapsed to one 3x3 (R is the c2w rotation stored by 3DGS)."""
+    _, _, K = HWK
+    return (np.asarray(R, np.float64) @ np.linalg.inv(np.asarray(K, np.float64))).astype(np.float32)
+
+
+class _ShadeSurfel(torch.autograd.Function):
+    """(base_color[3,H,W], features[S,H,W], allmap[7,H,W], *levels) ->
+    (final, specular, direct_light, normal_world, diffuse), each [3,H,W]."""
+
+    @staticmethod
+    def forward(ctx, base_color, features, allmap, bg, cfg, *levels):
+        lib = _lib.load()
+        dev = base_color.device
+        M, Q, min_r, max_r, srgb = cfg
+        base_color, features, allmap = base_color.contiguous(), features.contiguous(), allmap.contiguous()
+        levels = tuple(l.contiguous() for l in levels)
+        if features.shape[0] < 5:
+            raise RuntimeError("features must hold at least refl, roughness and albedo planes")
+        H, W = base_color.shape[1], base_color.shape[2]
+        a = _chain_args(levels, min_r, max_r)
+        a.width, a.height, a.srgb = W, H, int(bool(srgb))
+        a.ray_matrix[:] = [float(v) for v in np.asarray(M, np.float32).reshape(-1)]
+        a.normal_matrix[:] = [float(v) for v in np.asarray(Q, np.float32).reshape(-1)]
+        lut = fg_lut(dev)
+        bg = bg.to(device=dev, dtype=torch.float32).contiguous()
+        outs = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(5)]
+        a.background, a.base_color, a.features, a.allmap, a.lut = (
+            bg.data_ptr(), base_color.data_ptr(), features.data_ptr(), allmap.data_ptr(), lut.data_ptr())
+        a.out_final, a.out_specular, a.out_direct, a.out_normal, a.out_diffuse = (o.data_ptr() for o in outs)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_shade_forward(C.byref(a), _stream(dev)), "mrgs_shade_forward")
+        ctx.cfg = cfg
+        ctx.save_for_backward(base_color, features, allmap, bg, *levels)
+        ctx.mark_non_differentiable(outs[2])
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_final, g_spec, g_direct, g_normal, g_diffuse):
+        lib = _lib.load()
+        base_color, features, allmap, bg, *levels = ctx.saved_tensors
+        dev = base_color.device
+        M, Q, min_r, max_r, srgb = ctx.cfg
+        H, W = base_color.shape[1], base_color.shape[2]
+        a = _chain_args(levels, min_r, max_r)
+        a.width, a.height, a.srgb = W, H, int(bool(srgb))
+        a.ray_matrix[:] = [float(v) for v in np.asarray(M, np.float32).reshape(-1)]
+        a.normal_matrix[:] = [float(v) for v in np.asarray(Q, np.float32).reshape(-1)]
+        lut = fg_lut(dev)
+        a.background, a.base_color, a.features, a.allmap, a.lut = (
+            bg.data_ptr(), base_color.data_ptr(), features.data_ptr(), allmap.data_ptr(), lut.data_ptr())
+        keep = [g.contiguous() for g in (g_final, g_spec, g_normal, g_diffuse)]
+        a.dL_dfinal, a.dL_dspecular, a.dL_dnormal, a.dL_ddiffuse = (g.data_ptr() for g in keep)
+        d_base = torch.empty_like(base_color)
+        d_feat = torch.zeros_like(features) if features.shape[0] > 5 else torch.empty_like(features)
+        d_allmap = torch.zeros_like(allmap)
+        d_levels = [torch.zeros_like(l) for l in levels]
+        a.dL_dbase_color, a.dL_dfeatures, a.dL_dallmap = d_base.data_ptr(), d_feat.data_ptr(), d_allmap.data_ptr()
+        for i, d in enumerate(d_levels):
+            a.dL_dlevels[i] = d.data_ptr()
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_shade_backward(C.byref(a), _stream(dev)), "mrgs_shade_backward")
+        return (d_base, d_feat, d_allmap, None, None, *d_levels)
+
+
+def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, HWK, R, bg_color,
+                 srgb: bool = False) -> dict:
+    """Everything render_surfel does after the rasterizer call except depth_to_normal
+    (gaussian_renderer/__init__.py:372-469). HWK = (H, W, K) and R (c2w rotation) come from the
+    camera exactly as the reference passes `viewpoint_camera.HWK / .R`."""
+    cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb)
+    final, specular, direct, normal_w, diffuse = _ShadeSurfel.apply(
+        rendered_image, rendered_features, allmap, bg_color, cfg, *envmap.specular)
+    return {
+        "render": final,
+        "refl_strength_map": rendered_features[:1],
+        "diffuse_map": diffuse,
+        "diffuse_map_ori": rendered_image,
+        "specular_map": specular,
+        "base_color_map": rendered_features[2:5],
+        "roughness_map": rendered_features[1:2],
+        "rend_alpha": allmap[1:2],
+        "rend_normal": normal_w,
+        "rend_dist": allmap[6:7],
+        "direct_light": direct,
+    }
+
+
+def get_specular_color_surfel(envmap: "EnvLight", albedo, HWK, R, T, normal_map, render_alpha,
+                              scaling_modifier=1.0, refl_strength=None, roughness=None, pc=None,
+                              surf_depth=None, indirect_light=None):
+    """utils/refl_utils.py:364-419 with the reference's HWC tensors; returns (specular [3,H,W],
+    {'direct_light', 'specular_weight'}). The ray-traced visibility branch is out of scope."""
+    if pc is not None and getattr(pc, "ray_tracer", None) is not None and indirect_light is not None:
+        raise NotImplementedError("mesh/OptiX visibility tracing stays on the reference")
+    H, W, _ = HWK
+    alpha = render_alpha.permute(2, 0, 1)
+    allmap = torch.zeros((7, H, W), dtype=torch.float32, device=albedo.device)
+    allmap[1:2] = alpha
+    allmap[2:5] = (normal_map * render_alpha.clamp_min(1e-6)).permute(2, 0, 1)
+    feats = torch.cat([refl_strength, roughness, albedo], -1).permute(2, 0, 1).contiguous()
+    cfg = (ray_matrix(HWK, R), np.eye(3, dtype=np.float32), envmap.min_roughness, envmap.max_roughness, False)
+    zero3 = torch.zeros((3, H, W), dtype=torch.float32, device=albedo.device)
+    _, specular, direct, _, _ = _ShadeSurfel.apply(zero3, feats, allmap, torch.zeros(3, device=albedo.device),
+                                                   cfg, *envmap.specular)
+    with torch.no_grad():
+        safe = (direct * alpha).clamp_min(1e-20)
+    extra = {"direct_light": direct, "specular_weight": (specular / safe).permute(1, 2, 0)}
+    return specular, extra
+
+
+class EnvLight(torch.nn.Module):
+    """Trainable logit-space cubemap with a GGX-prefiltered mip chain (scene/light.py:21-129)."""
+
+    def __init__(self, path=None, device=None, scale=1.0, min_res=16, max_res=128, min_roughness=0.08,
+                 max_roughness=0.5, trainable=False):
+        super().__init__()
+        if path is not None:
+            raise NotImplementedError("loading .hdr/.exr environment maps stays on the reference")
+        self.device = device if device is not None else "cuda"
+        self.scale = scale
+        self.min_res, self.max_res = min_res, max_res
+        self.min_roughness, self.max_roughness = min_roughness, max_roughness
+        self.trainable = trainable
+        self.base = torch.nn.Parameter(
+            torch.zeros(6, max_res, max_res, 3, dtype=torch.float32, device=self.device),
+            requires_grad=trainable)
+        self.build_mips()
+
+    def build_mips(self, cutoff=0.99):
+        from . import cubemap as cm
+        self.specular = [self.base]
+        while self.specular[-1].shape[1] > self.min_res:
+            self.specular += [cm.cubemap_mip(self.specular[-1])]
+        self.diffuse = cm.diffuse_cubemap(self.specular[-1])
+        n = len(self.specular)
+        for idx in range(n - 1):
+            roughness = (idx / (n - 2)) * (self.max_roughness - self.min_roughness) + self.min_roughness
+            self.specular[idx] = cm.specular_cubemap(self.specular[idx], roughness, cutoff)
+        self.specular[-1] = cm.specular_cubemap(self.specular[-1], 1.0, cutoff)
+
+    def set_chain(self, levels):
+        """Install an externally built mip chain (tests / benchmarks)."""
+        self.specular = list(levels)
+
+    def get_mip(self, roughness):
+        n = len(self.specular)
+        return torch.where(
+            roughness < self.max_roughness,
+            (torch.clamp(roughness, self.min_roughness, self.max_roughness) - self.min_roughness)
+            / (self.max_roughness - self.min_roughness) * (n - 2),
+            (torch.clamp(roughness, self.max_roughness, 1.0) - self.max_roughness)
+            / (1.0 - self.max_roughness) + n - 2)
+
+    def forward(self, l, mode=None, roughness=None):
+        """Query the environment light for directions l[..., 3] (forward only; gradients reach the
+        cubemap through shade_surfel)."""
+        lib = _lib.load()
+        prefix = l.shape[:-1]
+        d = l.detach().reshape(-1, 3).contiguous().float()
+        out = torch.empty_like(d)
+        if mode == "diffuse":
+            levels = [self.diffuse, self.diffuse[:, ::1]] if False else [self.diffuse]
+        elif mode == "pure_env":
+            levels = [self.base]
+        else:
+            levels = self.specular
+        rough = None
+        if mode not in ("diffuse", "pure_env") and roughness is not None:
+            rough = roughness.detach().reshape(-1).contiguous().float()
+        if len(levels) == 1:  # the ABI wants >= 2 levels; duplicate is never read without roughness
+            small = torch.nn.functional.avg_pool2d(levels[0].detach().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
+            levels = [levels[0].detach().contiguous(), small]
+        a = _chain_args([x.detach().contiguous() for x in levels], self.min_roughness, self.max_roughness)
+        with torch.cuda.device(d.device):
+            _lib.check(lib.mrgs_envlight_query(C.byref(a), d.shape[0], d.data_ptr(),
+                                               None if rough is None else rough.data_ptr(), out.data_ptr(),
+                                               _stream(d.device)), "mrgs_envlight_query")
+        return out.view(*prefix, 3)
+
+
+def smoke_check(dev) -> None:
+    """Tiny forward+backward of the fused shader against the torch restatement (used by smoke())."""
+    from materialrefgs_b200 import synthetic
+    from oracle import shading_oracle as so
+    H, W = 64, 96
+    cam = synthetic.orbit_camera(1, 8, W, H)
+    base, feats, allmap = so.synthetic_gbuffer(H, W, device="cpu")
+    levels = so.synthetic_chain(64, 16)
+    bg = torch.tensor([0.2, 0.4, 0.6])
+    ref = so.shade_surfel(so.EnvLightOracle(levels), so.load_lut(), base, feats, allmap, cam, bg)
+    env = EnvLight.__new__(EnvLight)
+    torch.nn.Module.__init__(env)
+    env.min_roughness, env.max_roughness = 0.08, 0.5
+    env.set_chain([l.to(dev) for l in levels])
+    out = shade_surfel(env, base.to(dev), feats.to(dev), allmap.to(dev), cam.HWK, cam.R, bg.to(dev))
+    err = (out["render"].cpu() - ref["render"]).abs().max().item()
+    assert err <= 1e-4, f"fused shading differs from the oracle by {err}"

@@ -83,5 +83,35 @@ def main():
         print(f"{name}: P={P} Pv={int(vis.sum())} R={R} contrib max {int(im['n_contrib'][0].max())}")
 
 
+def cubemap_golden(out):
+    """Golden vectors of the cubemap prefilter from the unmodified renderutils_plugin."""
+    import importlib
+    plug_dir = ROOT / "oracle" / "_ref" / "renderutils_plugin"
+    if not (plug_dir / "renderutils_plugin.so").exists():
+        print("renderutils_plugin not built; skipping cubemap golden")
+        return
+    sys.path.insert(0, str(plug_dir))
+    plug = importlib.import_module("renderutils_plugin")
+    sys.path.insert(0, str(ROOT))
+    from oracle import cubemap_oracle as co
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(21)
+    for N, rough in ((16, 0.3), (16, 1.0), (32, 0.08)):
+        cube = torch.randn(6, N, N, 3, generator=g).to(dev)
+        dout = torch.randn(6, N, N, 4, generator=g).to(dev)
+        ct = co.ndf_cutoff_costheta(rough, 0.99)
+        bounds = plug.specular_bounds(N, ct)
+        spec = plug.specular_cubemap_fwd(cube, bounds, rough, ct)
+        dspec = plug.specular_cubemap_bwd(cube, bounds, dout, rough, ct)
+        diff = plug.diffuse_cubemap_fwd(cube)
+        ddiff = plug.diffuse_cubemap_bwd(cube, dout[..., :3].contiguous())
+        n = lambda t: t.detach().cpu().numpy()
+        np.savez_compressed(out / f"cubemap_n{N}_r{int(rough * 100):03d}.npz", N=N, roughness=rough, cutoff=0.99,
+                            costheta=ct, cube=n(cube), dout=n(dout), bounds=n(bounds), spec4=n(spec),
+                            dspec=n(dspec), diffuse=n(diff), ddiffuse=n(ddiff))
+        print(f"cubemap golden N={N} r={rough}: wsum mean {float(spec[..., 3].mean()):.5f}")
+
+
 if __name__ == "__main__":
     main()
+    cubemap_golden(Path(sys.argv[sys.argv.index("--out") + 1]) if "--out" in sys.argv else Path("gpurun_out/golden"))
