@@ -216,7 +216,7 @@ class EnvLight(torch.nn.Module):
         d = l.detach().reshape(-1, 3).contiguous().float()
         out = torch.empty_like(d)
         if mode == "diffuse":
-            levels = [self.diffuse, self.diffuse[:, ::1]] if False else [self.diffuse]
+            levels = [self.diffuse]
         elif mode == "pure_env":
             levels = [self.base]
         else:

@@ -61,8 +61,10 @@ def test_against_numpy_oracle():
     g = torch.Generator().manual_seed(2)
     cube = torch.randn(6, N, N, 3, generator=g)
     rgb_ref, out4_ref, ct = co.specular_cubemap(cube.numpy(), rough)
-    out = cm.specular_cubemap(cube.to(DEV), rough)
-    assert np.abs(out.cpu().numpy() - rgb_ref).max() <= 1e-5
+    out = cm.specular_cubemap(cube.to(DEV), rough).cpu().numpy()
+    # N = 8 < the 16x16 culling tile: the reference's interval test empties some bounds -> 0/0
+    assert np.array_equal(np.isnan(out), np.isnan(rgb_ref))
+    assert np.nanmax(np.abs(out - rgb_ref)) <= 1e-5
     assert np.array_equal(cm.specular_bounds(N, ct, DEV).cpu().numpy(), co.specular_bounds(N, ct))
     assert np.abs(cm.diffuse_cubemap(cube.to(DEV)).cpu().numpy() - co.diffuse_cubemap(cube.numpy())).max() <= 1e-5
 
