@@ -1,0 +1,93 @@
+"""CPU, world_size 2, gloo: the host logic of the view-sharded step (materialrefgs_b200/parallel.py).
+The per-view renderer is a deterministic stand-in; what is checked is the sharding, the arena layout,
+the single sum-allreduce, and the densification semantics of scene/gaussian_model.py:1059-1061 +
+train_refnerf.py:1416-1418 (norm per view, then summed; visibility count; max radii)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from materialrefgs_b200 import parallel
+
+P, NV = 37, 5
+
+
+def fake_view(i):
+    g = torch.Generator().manual_seed(100 + i)
+    grads = {name: torch.randn(P, w, generator=g) for name, w in parallel.GRAD_FIELDS}
+    grads["shs"] = grads["shs"].view(P, 16, 3)
+    radii = torch.randint(-1, 30, (P,), generator=g, dtype=torch.int32).clamp_min(0)
+    return {"grads": grads, "viewspace_grad": torch.randn(P, 3, generator=g), "radii": radii}
+
+
+def expected():
+    flat = torch.zeros(P, sum(w for _, w in parallel.GRAD_FIELDS))
+    stats = torch.zeros(P, 2)
+    mx = torch.zeros(P, dtype=torch.int32)
+    for i in range(NV):
+        v = fake_view(i)
+        flat += torch.cat([v["grads"][n].reshape(P, -1) for n, _ in parallel.GRAD_FIELDS], 1)
+        vis = v["radii"] > 0
+        stats[:, 0] += torch.linalg.norm(v["viewspace_grad"][:, :2], dim=-1) * vis
+        stats[:, 1] += vis.float()
+        mx = torch.maximum(mx, v["radii"])
+    return flat, stats, mx
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        arena = parallel.GradArena.create(P, "cpu")
+        seen = []
+
+        def render(i):
+            seen.append(i)
+            return fake_view(i)
+        views = parallel.train_step_view_sharded(render, NV, arena)
+        ev = parallel.eval_views_sharded(lambda i: torch.tensor(float(i)), 7)
+        q.put((rank, seen, arena.flat.clone(), arena.stats.clone(), arena.max_radii.clone(),
+               sorted(ev.keys()), views["shs"].shape))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.timeout(120)
+def test_view_sharded_step_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    flat, stats, mx = expected()
+    assert res[0][1] == [0, 2, 4] and res[1][1] == [1, 3]          # round-robin, disjoint, complete
+    for rank, seen, f, s, m, ev_keys, shs_shape in res:
+        assert torch.allclose(f, flat, atol=1e-5)
+        assert torch.allclose(s, stats, atol=1e-5)
+        assert torch.equal(m, mx)
+        assert ev_keys == list(range(rank, 7, 2))
+        assert tuple(shs_shape) == (P, 48)
+
+
+def test_single_process_is_the_plain_sum():
+    arena = parallel.GradArena.create(P, "cpu")
+    parallel.train_step_view_sharded(fake_view, NV, arena)
+    flat, stats, mx = expected()
+    assert torch.allclose(arena.flat, flat, atol=1e-5) and torch.allclose(arena.stats, stats, atol=1e-5)
+    assert torch.equal(arena.max_radii, mx)
+    assert parallel.shard_views(10, 3, 4) == [3, 7]
