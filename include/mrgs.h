@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 1
+#define MRGS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -75,12 +75,15 @@ typedef void* (*mrgs_alloc_fn)(void* ctx, size_t bytes);
 /* Byte offsets of the sub-arrays inside the caller-owned scratch buffers. Exposed so tests
  * can decode tile keys / sorted ids / ranges / contributor counts bit-for-bit. */
 typedef struct MrgsGeomLayout {
-    size_t rec;           /* float [P][16]: Tu.xyz Tw.x | Tv.xyz Tw.y | Tw.z xy.x xy.y opacity | n.xyz depth */
+    size_t rec;           /* float [P][16]: Tu.xyz Tw.x | Tv.xyz Tw.y | Tw.z xy.x xy.y opacity | n.xyz tau    */
     size_t cf;            /* float [P][cf_stride]: rgb(3) features(S) zero padding                       */
     size_t clamped;       /* uint8 [P]: bit c set when SH colour channel c was clamped to 0             */
     size_t tiles_touched; /* uint32[P]                                                                    */
     size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched                              */
     size_t rect;          /* uint32[P][2]: (min.x | min.y<<16), (max.x | max.y<<16) tile rectangle        */
+    size_t depth;         /* float [P]: view-space depth p_view.z (the low 32 key bits)                   */
+    size_t bbox;          /* float [P][4]: conservative pixel bounds (xmin,ymin,xmax,ymax) of the region
+                             where the surfel's alpha can reach 1/255; used for per-warp culling          */
     size_t scan_temp;     /* scan scratch                                                                 */
     size_t scan_temp_bytes;
     size_t total;         /* bytes required                                                               */

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 1
+MRGS_ABI_VERSION = 2
 MAX_FEATURES = 24
 TILE = 16
 
@@ -21,7 +21,7 @@ alloc_fn = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 class GeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "rec", "cf", "clamped", "tiles_touched", "point_offsets", "rect", "scan_temp",
+        "rec", "cf", "clamped", "tiles_touched", "point_offsets", "rect", "depth", "bbox", "scan_temp",
         "scan_temp_bytes", "total")] + [("cf_stride", C.c_int32)]
 
 

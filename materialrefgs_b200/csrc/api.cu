@@ -132,6 +132,8 @@ int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out) {
     out->tiles_touched = off; off = align_up(off + n * sizeof(uint32_t));
     out->point_offsets = off; off = align_up(off + n * sizeof(uint32_t));
     out->rect = off;          off = align_up(off + n * sizeof(uint2));
+    out->depth = off;         off = align_up(off + n * sizeof(float));
+    out->bbox = off;          off = align_up(off + n * sizeof(float4));
     out->scan_temp = off;
     out->scan_temp_bytes = scan_temp_bytes(P > 0 ? P : 1);
     off = align_up(off + out->scan_temp_bytes);
@@ -286,6 +288,8 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         pp.clamped = (uint8_t*)(geom + gl.clamped);
         pp.tiles_touched = (uint32_t*)(geom + gl.tiles_touched);
         pp.rect = (uint2*)(geom + gl.rect);
+        pp.depth = (float*)(geom + gl.depth);
+        pp.bbox = (float4*)(geom + gl.bbox);
         uint32_t* offsets = (uint32_t*)(geom + gl.point_offsets);
 
         {
@@ -339,7 +343,7 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
 
             {
                 StageScope sc(MRGS_STAGE_DUPLICATE, stream, 1);
-                launch_duplicate_with_keys(a->P, pp.rec, pp.rect, a->radii, offsets, keys_unsorted,
+                launch_duplicate_with_keys(a->P, pp.depth, pp.rect, a->radii, offsets, keys_unsorted,
                                            vals_unsorted, grid_x, stream);
             }
             MRGS_LAUNCH_OK("duplicate_with_keys", stream, debug);
@@ -363,6 +367,7 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         }
         rp.rec = pp.rec;
         rp.cf = pp.cf;
+        rp.bbox = pp.bbox;
     }
     a->num_rendered = R;
 
@@ -545,6 +550,7 @@ int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
         rp.point_list = (const uint32_t*)(bin + bl.point_list);
         rp.rec = (const float*)(geom + gl.rec);
         rp.cf = (const float*)(geom + gl.cf);
+        rp.bbox = (const float4*)(geom + gl.bbox);
         rp.background = a->background;
         rp.state = (const float*)(img + il.state);
         rp.dL_dcolor = a->dL_dout_color;

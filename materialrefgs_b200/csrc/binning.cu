@@ -55,7 +55,7 @@ int run_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* 
 namespace {
 
 __global__ void __launch_bounds__(256)
-duplicate_with_keys_kernel(int P, const float* __restrict__ rec, const uint2* __restrict__ rect,
+duplicate_with_keys_kernel(int P, const float* __restrict__ depth, const uint2* __restrict__ rect,
                            const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
                            uint64_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -64,7 +64,7 @@ duplicate_with_keys_kernel(int P, const float* __restrict__ rec, const uint2* __
     uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
     const uint2 r = rect[idx];
     const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-    const uint32_t depth_bits = __float_as_uint(rec[(size_t)idx * kGeomFloats + 15]);
+    const uint32_t depth_bits = __float_as_uint(depth[idx]);
     for (int y = y0; y < y1; ++y) {
         for (int x = x0; x < x1; ++x) {
             const uint64_t key = ((uint64_t)(uint32_t)(y * grid_x + x) << 32) | depth_bits;
@@ -94,10 +94,10 @@ identify_tile_ranges_kernel(int R, const uint64_t* __restrict__ keys, uint2* __r
 
 }  // namespace
 
-void launch_duplicate_with_keys(int P, const float* rec, const uint2* rect, const int* radii,
+void launch_duplicate_with_keys(int P, const float* depth, const uint2* rect, const int* radii,
                                 const uint32_t* offsets, uint64_t* keys, uint32_t* values,
                                 int grid_x, cudaStream_t stream) {
-    duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, rec, rect, radii, offsets,
+    duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, depth, rect, radii, offsets,
                                                                     keys, values, grid_x);
 }
 

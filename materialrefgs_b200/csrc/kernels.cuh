@@ -28,6 +28,8 @@ struct PreprocessParams {
     uint8_t* clamped;
     uint32_t* tiles_touched;
     uint2* rect;
+    float* depth;
+    float4* bbox;
 };
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
@@ -39,7 +41,7 @@ size_t scan_temp_bytes(int P);
 size_t sort_temp_bytes(int64_t R);
 int run_inclusive_scan(const uint32_t* in, uint32_t* out, int P, void* temp, size_t temp_bytes,
                        cudaStream_t stream);
-void launch_duplicate_with_keys(int P, const float* rec, const uint2* rect, const int* radii,
+void launch_duplicate_with_keys(int P, const float* depth, const uint2* rect, const int* radii,
                                 const uint32_t* offsets, uint64_t* keys, uint32_t* values,
                                 int grid_x, cudaStream_t stream);
 int run_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
@@ -55,6 +57,7 @@ struct RenderFwdParams {
     const uint32_t* point_list;
     const float* rec;
     const float* cf;
+    const float4* bbox;
     const float* background;
     float* state;  // [tiles][5][256]
     float* out_color;
@@ -69,6 +72,7 @@ struct RenderBwdParams {
     const uint32_t* point_list;
     const float* rec;
     const float* cf;
+    const float4* bbox;
     const float* background;
     const float* state;
     const float* dL_dcolor;

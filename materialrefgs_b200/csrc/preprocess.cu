@@ -167,11 +167,17 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
     }
     p.clamped[idx] = (uint8_t)clamped_bits;
 
+    const float opacity = p.opacities[idx];
+    float tau;
+    const float4 bb = alpha_support_bounds(T, cx, cy, opacity, tau);
+
     float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * kGeomFloats);
     rec[0] = make_float4(T[0], T[1], T[2], T[6]);
     rec[1] = make_float4(T[3], T[4], T[5], T[7]);
-    rec[2] = make_float4(T[8], cx, cy, p.opacities[idx]);
-    rec[3] = make_float4(normal.x, normal.y, normal.z, pv.z);
+    rec[2] = make_float4(T[8], cx, cy, opacity);
+    rec[3] = make_float4(normal.x, normal.y, normal.z, tau);
+    p.depth[idx] = pv.z;
+    p.bbox[idx] = bb;
 
     p.rect[idx] = make_uint2((unsigned)x0 | ((unsigned)y0 << 16), (unsigned)x1 | ((unsigned)y1 << 16));
     p.radii[idx] = radius;

@@ -4,9 +4,11 @@
 //
 // Behavioural reference: renderCUDA rast/cuda_rasterizer/backward.cu:145-468 (same skip tests,
 // same recurrences). Own design:
-//   * the traversal starts at the tile's largest `last_contributor` instead of the list end,
-//     and each warp (8x4 pixel block) starts at its own largest one — instances nobody blended
-//     are neither staged nor evaluated;
+//   * warp-autonomous traversal without CTA barriers (see render_fwd.cu): each warp (8x4 pixel block)
+//     starts at its own largest `last_contributor` — instances nobody blended are neither staged nor
+//     evaluated — walks back to front 32 instances per step, culls them against the surfel's
+//     conservative alpha-support box (1/32 of an instruction stream per instance) and stages only
+//     the survivors' records in its private shared-memory slots;
 //   * gradients of one instance are summed across the 32 pixels of a warp with a transposing
 //     butterfly (31 shuffles for up to 32 values, lane l ends up owning value l) and leave the
 //     warp as ONE coalesced red.global.add per instance instead of 16+S same-address atomics
@@ -45,16 +47,12 @@ render_bwd_kernel(const RenderBwdParams p) {
     constexpr int NC = NQ * 4;           // colour + feature (+ padding) channels
     constexpr int NV = kGradColor + NC;  // values per instance incl. padding channels
     constexpr bool kTwoPass = NV > 32;
-    __shared__ float4 s_g0[kBatch];
-    __shared__ float4 s_g1[kBatch];
-    __shared__ float4 s_g2[kBatch];
-    __shared__ float4 s_g3[kBatch];
-    __shared__ float4 s_cf[NQ][kBatch];
-    __shared__ uint32_t s_id[kBatch];
-    __shared__ int s_max_last;
+    __shared__ float4 s_g[kWarpsPerTile][4][32];
+    __shared__ float4 s_cf[kWarpsPerTile][NQ][32];
+    __shared__ uint32_t s_id[kWarpsPerTile][32];
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31;
+    const int lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
     const int px = blockIdx.x * kTileX + slot_x(tid);
     const int py = blockIdx.y * kTileY + slot_y(tid);
@@ -62,8 +60,11 @@ render_bwd_kernel(const RenderBwdParams p) {
     const float pxf = (float)px, pyf = (float)py;
     const size_t HW = (size_t)p.H * p.W;
     const size_t pix = (size_t)py * p.W + px;
+    const float bx0 = (float)(blockIdx.x * kTileX + (warp & 1) * 8), bx1 = bx0 + 7.0f;
+    const float by0 = (float)(blockIdx.y * kTileY + (warp >> 1) * 4), by1 = by0 + 3.0f;
 
     const uint2 range = p.ranges[tile];
+    const uint32_t* __restrict__ list = p.point_list + range.x;
 
     const float* st = p.state + (size_t)tile * (5 * kTilePixels) + tid;
     const float T_final = inside ? st[0] : 0.0f;
@@ -73,13 +74,9 @@ render_bwd_kernel(const RenderBwdParams p) {
     const int median_contributor = inside ? (int)reinterpret_cast<const uint32_t*>(st)[4 * kTilePixels] : 0;
     const float final_A = 1.0f - T_final;
 
-    if (tid == 0) s_max_last = 0;
-    __syncthreads();
+    // entries [0, warp_last) of the tile's list were blended by at least one pixel of this warp
     const int warp_last = __reduce_max_sync(kFull, last_contributor);
-    if (lane == 0 && warp_last > 0) atomicMax(&s_max_last, warp_last);
-    __syncthreads();
-    const int n_eff = s_max_last;  // entries [0, n_eff) of this tile's list were blended by someone
-    if (n_eff == 0) return;
+    if (warp_last == 0) return;
 
     float dL_dpix[NC];
 #pragma unroll
@@ -118,35 +115,49 @@ render_bwd_kernel(const RenderBwdParams p) {
 
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(p.cf);
-    const int rounds = (n_eff + kBatch - 1) / kBatch;
 
-    for (int i = 0; i < rounds; ++i) {
-        __syncthreads();
-        const int first = n_eff - 1 - i * kBatch;  // list entry staged in slot 0
-        {
-            const int e = first - tid;
-            if (e >= 0) {
-                const uint32_t id = p.point_list[range.x + e];
-                s_id[tid] = id;
-                const float4* r = rec4 + (size_t)id * (kGeomFloats / 4);
-                s_g0[tid] = r[0];
-                s_g1[tid] = r[1];
-                s_g2[tid] = r[2];
-                s_g3[tid] = r[3];
-                const float4* c = cf4 + (size_t)id * NQ;
-#pragma unroll
-                for (int q = 0; q < NQ; ++q) s_cf[q][tid] = c[q];
-            }
+    // back-to-front in steps of 32 list entries; lane l of a step holds entry hi-1-l, so walking the
+    // survivor mask from bit 0 upwards visits entries in descending order
+    uint32_t id_next = 0;
+    float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (warp_last - 1 - lane >= 0) {
+        id_next = list[warp_last - 1 - lane];
+        bb_next = p.bbox[id_next];
+    }
+
+    for (int hi = warp_last; hi > 0; hi -= 32) {
+        const uint32_t id = id_next;
+        const float4 bb = bb_next;
+        const int e_mine = hi - 1 - lane;
+        const int e_next = e_mine - 32;
+        if (e_next >= 0) {
+            id_next = list[e_next];
+            bb_next = p.bbox[id_next];
         }
-        __syncthreads();
+        const bool keep = (e_mine >= 0) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0);
+        unsigned mask = __ballot_sync(kFull, keep);
+        if (mask == 0) continue;
+        if (keep) {
+            s_id[warp][lane] = id;
+            const float4* r = rec4 + (size_t)id * (kGeomFloats / 4);
+            s_g[warp][0][lane] = r[0];
+            s_g[warp][1][lane] = r[1];
+            s_g[warp][2][lane] = r[2];
+            s_g[warp][3][lane] = r[3];
+            const float4* c = cf4 + (size_t)id * NQ;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) s_cf[warp][q][lane] = c[q];
+        }
+        __syncwarp();
 
-        const int n = min(kBatch, first + 1);
-        // entries >= warp_last were blended by no pixel of this warp
-        for (int j = max(0, first - (warp_last - 1)); j < n; ++j) {
-            const int e = first - j;
-            const float4 g0 = s_g0[j], g1 = s_g1[j], g2 = s_g2[j];
+        while (mask != 0) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const int e = hi - 1 - j;
+            const float4 g0 = s_g[warp][0][j], g1 = s_g[warp][1][j], g2 = s_g[warp][2][j];
+            const float4 g3 = s_g[warp][3][j];
             SplatHit h;
-            const bool valid = (e < last_contributor) && ray_splat(g0, g1, g2, pxf, pyf, h);
+            const bool valid = (e < last_contributor) && ray_splat(g0, g1, g2, g3.w, pxf, pyf, h);
             if (!__any_sync(kFull, valid)) continue;
 
             float v[32];
@@ -165,7 +176,7 @@ render_bwd_kernel(const RenderBwdParams p) {
                 float dL_dalpha = 0.0f;
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    const float4 cv = s_cf[q][j];
+                    const float4 cv = s_cf[warp][q][j];
                     const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
@@ -202,7 +213,6 @@ render_bwd_kernel(const RenderBwdParams p) {
                 accum_alpha_rec = last_alpha + (1.0f - last_alpha) * accum_alpha_rec;
                 dL_dalpha += (1.0f - accum_alpha_rec) * dL_daccum;
 
-                const float4 g3 = s_g3[j];
                 an0 = last_alpha * ln0 + (1.0f - last_alpha) * an0;
                 an1 = last_alpha * ln1 + (1.0f - last_alpha) * an1;
                 an2 = last_alpha * ln2 + (1.0f - last_alpha) * an2;
@@ -254,7 +264,7 @@ render_bwd_kernel(const RenderBwdParams p) {
                 v[kGradOpacity] = G * dL_dalpha;
             }
 
-            float* row = p.grad_arena + (size_t)s_id[j] * p.grad_stride;
+            float* row = p.grad_arena + (size_t)s_id[warp][j] * p.grad_stride;
             const int n_live = kGradFeature + p.S;  // padding channels carry no gradient
             const float total = warp_transpose_reduce<(NV < 32 ? NV : 32)>(v, lane);
             if (lane < min(n_live, 32)) atomicAdd(row + lane, total);
@@ -263,6 +273,7 @@ render_bwd_kernel(const RenderBwdParams p) {
                 if (32 + lane < n_live) atomicAdd(row + 32 + lane, total2);
             }
         }
+        __syncwarp();  // all lanes are past their reads before the slots are overwritten
     }
 }
 

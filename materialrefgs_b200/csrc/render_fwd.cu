@@ -3,10 +3,21 @@
 //
 // Behavioural reference: renderCUDA rast/cuda_rasterizer/forward.cu:272-463 (per-pixel
 // arithmetic and skip/termination tests are reproduced bit-for-bit through ray_splat()).
-// Own design: one CTA per 16x16 tile with each warp owning an 8x4 pixel block; a batch of 256
-// instances is staged into shared memory as whole 16-byte vectors of the packed geometry and
-// colour/feature records (no per-pair global gathers in the blend loop); per-pixel state is
-// kept tile-major so every warp store is one full 128-byte line.
+//
+// Own design — WARP-AUTONOMOUS traversal, no CTA-wide barriers:
+//   * one CTA per 16x16 tile, each of its 8 warps owns an 8x4 pixel block and walks the tile's
+//     instance list on its own, 32 instances per step (lane <-> instance);
+//   * per step every lane fetches its instance id and the surfel's conservative alpha-support box
+//     (16 B, computed once per surfel in preprocess) and tests it against the warp's pixel block:
+//     the cull costs 1/32 of an instruction stream per (warp, instance) instead of a full ray-splat
+//     evaluation by all 32 pixels. Survivors (ballot) have their packed 64-B geometry and
+//     colour/feature records staged into the warp's private shared-memory slots as 16-byte
+//     vectors, then the 32 pixels blend them in list order with broadcast LDS.128 reads;
+//   * the next step's ids/boxes are prefetched while the current survivors are blended;
+//   * a warp stops as soon as its 32 pixels are saturated (the reference needs all 256 of the tile);
+//   * culling and the in-lane early rejection are conservative by construction (splat_math.cuh), so
+//     n_contrib / final_T stay bit-identical to the reference;
+//   * per-pixel state is stored tile-major so each warp store is one full 128-byte line.
 #include "kernels.cuh"
 #include "splat_math.cuh"
 
@@ -14,29 +25,31 @@ namespace mrgs {
 
 namespace {
 
+constexpr unsigned kFullMask = 0xffffffffu;
+
 template <int NQ>
 __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwdParams p) {
-    __shared__ float4 s_g0[kBatch];
-    __shared__ float4 s_g1[kBatch];
-    __shared__ float4 s_g2[kBatch];
-    __shared__ float4 s_g3[kBatch];
-    __shared__ float4 s_cf[NQ][kBatch];
+    __shared__ float4 s_g[kWarpsPerTile][4][32];
+    __shared__ float4 s_cf[kWarpsPerTile][NQ][32];
 
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
     const int px = blockIdx.x * kTileX + slot_x(tid);
     const int py = blockIdx.y * kTileY + slot_y(tid);
     const bool inside = px < p.W && py < p.H;
     const float pxf = (float)px, pyf = (float)py;
+    // pixel block of this warp (inclusive bounds, pixel-index coordinates)
+    const float bx0 = (float)(blockIdx.x * kTileX + (warp & 1) * 8), bx1 = bx0 + 7.0f;
+    const float by0 = (float)(blockIdx.y * kTileY + (warp >> 1) * 4), by1 = by0 + 3.0f;
 
     const uint2 range = p.ranges[tile];
     const int count = (int)(range.y - range.x);
-    const int rounds = (count + kBatch - 1) / kBatch;
-    int toDo = count;
+    const uint32_t* __restrict__ list = p.point_list + range.x;
 
     bool done = !inside;
     float T = 1.0f;
-    uint32_t contributor = 0, last_contributor = 0, median_contributor = 0;
+    uint32_t last_contributor = 0, median_contributor = 0;
     float acc[NQ * 4];
 #pragma unroll
     for (int c = 0; c < NQ * 4; ++c) acc[c] = 0.0f;
@@ -46,33 +59,50 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(p.cf);
 
-    for (int i = 0; i < rounds; ++i, toDo -= kBatch) {
-        if (__syncthreads_count(done) == kTilePixels) break;
+    // software pipeline: (id, box) of the step after the current one
+    uint32_t id_next = 0;
+    float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f);
+    if (lane < count) {
+        id_next = list[lane];
+        bb_next = p.bbox[id_next];
+    }
 
-        const int progress = i * kBatch + tid;
-        if (progress < count) {
-            const uint32_t id = p.point_list[range.x + progress];
+    for (int base = 0; base < count; base += 32) {
+        if (__all_sync(kFullMask, done)) break;
+        const uint32_t id = id_next;
+        const float4 bb = bb_next;
+        const int e_next = base + 32 + lane;
+        if (e_next < count) {
+            id_next = list[e_next];
+            bb_next = p.bbox[id_next];
+        }
+        const bool keep = (base + lane < count) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0);
+        unsigned mask = __ballot_sync(kFullMask, keep);
+        if (mask == 0) continue;
+        if (keep) {
             const float4* r = rec4 + (size_t)id * (kGeomFloats / 4);
-            s_g0[tid] = r[0];
-            s_g1[tid] = r[1];
-            s_g2[tid] = r[2];
-            s_g3[tid] = r[3];
+            s_g[warp][0][lane] = r[0];
+            s_g[warp][1][lane] = r[1];
+            s_g[warp][2][lane] = r[2];
+            s_g[warp][3][lane] = r[3];
             const float4* c = cf4 + (size_t)id * NQ;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) s_cf[q][tid] = c[q];
+            for (int q = 0; q < NQ; ++q) s_cf[warp][q][lane] = c[q];
         }
-        __syncthreads();
+        __syncwarp();
 
-        const int n = min(kBatch, toDo);
-        for (int j = 0; !done && j < n; ++j) {
-            ++contributor;
+        while (mask != 0 && !done) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float4 g3 = s_g[warp][3][j];
             SplatHit h;
-            if (!ray_splat(s_g0[j], s_g1[j], s_g2[j], pxf, pyf, h)) continue;
+            if (!ray_splat(s_g[warp][0][j], s_g[warp][1][j], s_g[warp][2][j], g3.w, pxf, pyf, h)) continue;
             const float test_T = __fmul_rn(T, __fadd_rn(1.0f, -h.alpha));
             if (test_T < kTMin) {
                 done = true;
                 continue;
             }
+            const uint32_t contributor = (uint32_t)(base + j + 1);
             const float w = __fmul_rn(h.alpha, T);
 
             const float A = __fadd_rn(1.0f, -T);
@@ -87,13 +117,12 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
                 median_depth = h.depth;
                 median_contributor = contributor;
             }
-            const float4 g3 = s_g3[j];
             N0 = __fmaf_rn(g3.x, w, N0);
             N1 = __fmaf_rn(g3.y, w, N1);
             N2 = __fmaf_rn(g3.z, w, N2);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
-                const float4 v = s_cf[q][j];
+                const float4 v = s_cf[warp][q][j];
                 acc[4 * q + 0] = __fmaf_rn(w, v.x, acc[4 * q + 0]);
                 acc[4 * q + 1] = __fmaf_rn(w, v.y, acc[4 * q + 1]);
                 acc[4 * q + 2] = __fmaf_rn(w, v.z, acc[4 * q + 2]);
@@ -102,6 +131,7 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
             T = test_T;
             last_contributor = contributor;
         }
+        __syncwarp();  // all lanes are past their reads before the slots are overwritten
     }
 
     // per-pixel state for the backward, tile-major planes: T, M1, M2, n_contrib, median index

@@ -152,6 +152,48 @@ __device__ __forceinline__ void tile_rect(float cx, float cy, int radius, int gr
                                 __fadd_rn(__fadd_rn(__fadd_rn(cy, rf), 16.0f), -1.0f), 0.0625f)));
 }
 
+// Conservative support of one surfel's alpha. A pair is blended only if
+//   alpha = min(0.99, opacity * exp(-min(rho3d, rho2d)/2)) >= 1/255  <=>  min(rho3d, rho2d) <= 2 ln(255 opacity) =: tau_exact.
+// tau = tau_exact * 1.001 + 0.001 leaves a margin ~1000x larger than the rounding of the fp32 path
+// (divisions, expf <= 2 ulp, logf), so "rho3d > tau and rho2d > tau" PROVES the exact evaluation would
+// have skipped the pair; results stay bit-identical (tests/test_raster_gpu.py compares n_contrib and
+// final_T bit-for-bit against the reference with the culling active).
+// The returned box bounds, in pixel coordinates, {rho3d <= tau} (projected ellipse, the reference's
+// compute_aabb formula with cutoff^2 = tau instead of 9) united with {rho2d <= tau} (disc of radius
+// sqrt(tau/2) around the 3-sigma centre), inflated by half a pixel. Surfels whose tau-ellipse reaches
+// the camera plane (unbounded projection) or whose box is numerically doubtful are never culled.
+__device__ __forceinline__ float4 alpha_support_bounds(const float* T, float cx, float cy, float opacity,
+                                                       float& tau) {
+    const float inf = __int_as_float(0x7f800000);
+    tau = 2.0f * logf(255.0f * opacity) * 1.001f + 0.001f;
+    if (!(tau > 0.0f)) {  // opacity < 1/255 (or NaN): alpha can never reach 1/255
+        if (!(tau <= 0.0f)) tau = inf;  // NaN opacity: disable every shortcut
+        return (tau == inf) ? make_float4(-inf, -inf, inf, inf) : make_float4(inf, inf, -inf, -inf);
+    }
+    const float4 everything = make_float4(-inf, -inf, inf, inf);
+    const float t6 = T[6], t7 = T[7], t8 = T[8];
+    const float d = tau * (t6 * t6 + t7 * t7) - t8 * t8;
+    if (!(d < -1e-4f * t8 * t8)) return everything;
+    const float rc = 1.0f / d;
+    const float fx = tau * rc, fz = -rc;
+    const float ex_c = fx * (T[0] * t6 + T[1] * t7) + fz * T[2] * t8;
+    const float ey_c = fx * (T[3] * t6 + T[4] * t7) + fz * T[5] * t8;
+    const float hx = ex_c * ex_c - (fx * (T[0] * T[0] + T[1] * T[1]) + fz * T[2] * T[2]);
+    const float hy = ey_c * ey_c - (fx * (T[3] * T[3] + T[4] * T[4]) + fz * T[5] * T[5]);
+    if (!(hx >= 0.0f) || !(hy >= 0.0f)) return everything;
+    const float ex = sqrtf(hx), ey = sqrtf(hy);
+    const float rlp = sqrtf(0.5f * tau);
+    const float mx = 0.5f + 1e-3f * (ex + rlp + fabsf(ex_c - cx));
+    const float my = 0.5f + 1e-3f * (ey + rlp + fabsf(ey_c - cy));
+    float4 bb;
+    bb.x = fminf(ex_c - ex, cx - rlp) - mx;
+    bb.y = fminf(ey_c - ey, cy - rlp) - my;
+    bb.z = fmaxf(ex_c + ex, cx + rlp) + mx;
+    bb.w = fmaxf(ey_c + ey, cy + rlp) + my;
+    if (!(bb.x <= bb.z) || !(bb.y <= bb.w)) return everything;  // NaN guard
+    return bb;
+}
+
 // Per (pixel, surfel) ray-splat evaluation shared by the forward and backward blend kernels.
 struct SplatHit {
     float kx, ky, kz, lx, ly, lz;  // the two homogeneous planes
@@ -166,7 +208,8 @@ struct SplatHit {
 
 // Returns false when the reference would `continue` (p.z == 0, depth < near, power > 0,
 // alpha < 1/255). g0 = (Tu.xyz, Tw.x), g1 = (Tv.xyz, Tw.y), g2 = (Tw.z, xy.x, xy.y, opacity).
-__device__ __forceinline__ bool ray_splat(const float4 g0, const float4 g1, const float4 g2,
+// `tau` is the surfel's conservative alpha-support threshold (alpha_support_bounds).
+__device__ __forceinline__ bool ray_splat(const float4 g0, const float4 g1, const float4 g2, const float tau,
                                           float pxf, float pyf, SplatHit& h) {
     const float Twx = g0.w, Twy = g1.w, Twz = g2.x;
     h.kx = __fmaf_rn(pxf, Twx, -g0.x);
@@ -179,13 +222,15 @@ __device__ __forceinline__ bool ray_splat(const float4 g0, const float4 g1, cons
     if (h.pz == 0.0f) return false;
     const float ppx = __fmaf_rn(h.ky, h.lz, -__fmul_rn(h.kz, h.ly));
     const float ppy = __fmaf_rn(h.kz, h.lx, -__fmul_rn(h.kx, h.lz));
-    h.sx = __fdiv_rn(ppx, h.pz);
-    h.sy = __fdiv_rn(ppy, h.pz);
-    h.rho3d = __fmaf_rn(h.sx, h.sx, __fmul_rn(h.sy, h.sy));
     h.dx = __fadd_rn(g2.y, -pxf);
     h.dy = __fadd_rn(g2.z, -pyf);
     const float d2 = __fmaf_rn(h.dy, h.dy, __fmul_rn(h.dx, h.dx));
     h.rho2d = __fadd_rn(d2, d2);
+    // provably-safe early rejection before the two IEEE divisions and the exp (see alpha_support_bounds)
+    if (h.rho2d > tau && (ppx * ppx + ppy * ppy) > tau * (h.pz * h.pz)) return false;
+    h.sx = __fdiv_rn(ppx, h.pz);
+    h.sy = __fdiv_rn(ppy, h.pz);
+    h.rho3d = __fmaf_rn(h.sx, h.sx, __fmul_rn(h.sy, h.sy));
     // !(rho3d > rho2d) in the binary is `rho3d <= rho2d` in the source; a NaN picks Tw.z
     h.depth = (h.rho3d <= h.rho2d)
                   ? __fadd_rn(Twz, __fmaf_rn(Twx, h.sx, __fmul_rn(Twy, h.sy)))

@@ -71,6 +71,8 @@ def _scene(P, S, W, H, opacity="trained", view=1, scale_mult=1.0):
     (100_000, 8, 800, 800, "trained"),
     (100_000, 0, 800, 800, "init"),
     (50_000, 11, 333, 517, "trained"),   # ragged image size, odd feature count
+    (1_000_000, 8, 800, 800, "trained"), # BASELINE size: culling / early rejection must stay exact
+    (300_000, 8, 800, 800, "init"),      # no early termination, long lists
 ])
 def test_forward_buffers_bit_exact(ref_ext, P, S, W, H, opacity):
     """Decode both libraries' scratch buffers and compare every binning artefact bit-for-bit."""
