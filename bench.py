@@ -73,9 +73,17 @@ class ClockSampler:
     def start(self):
         try:
             self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                       "-lms", "100", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
+                                       "-lms", "25", "-i", str(self.gpu)], stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+
+    def mark(self):
+        """Samples recorded before this point belong to set-up / warm-up and are dropped."""
+        try:
+            self.f.flush()
+            self.skip = len(Path(self.f.name).read_text().strip().splitlines())
+        except Exception:
+            self.skip = 0
 
     def stop(self) -> dict:
         if self.p is None:
@@ -87,7 +95,8 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        rows = [r.split(",") for r in Path(self.f.name).read_text().strip().splitlines() if r.count(",") >= 8]
+        lines = Path(self.f.name).read_text().strip().splitlines()[getattr(self, "skip", 0):]
+        rows = [r.split(",") for r in lines if r.count(",") >= 8]
         os.unlink(self.f.name)
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
@@ -305,7 +314,7 @@ def cpu_shading_baseline():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -348,14 +357,16 @@ def main():
     lib = _lib.load()
 
     # ---- device-resident timing -------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()           # started before the warm-up so its own start-up cost is not timed
     for i in range(a.warmup):
         stepper.step(i)
     barrier(world_eff)
     lib.mrgs_profile_enable(1)
     lib.mrgs_profile_reset()
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier(world_eff)
     e0.record()

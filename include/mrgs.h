@@ -179,11 +179,11 @@ typedef struct MrgsBackwardArgs {
     const float* dL_dout_others;   /* [7,H,W]                                           */
     /* outputs: every element is written by the call (no pre-zeroing needed) */
     float* dL_dmeans2D;   /* [P,3]  densification proxy in .xy, 0 in .z                 */
-    float* dL_dcolors;    /* [P,3]                                                      */
+    float* dL_dcolors;    /* [P,3]  or NULL when not wanted                              */
     float* dL_dfeatures;  /* [P,S]                                                      */
     float* dL_dopacity;   /* [P]                                                        */
     float* dL_dmeans3D;   /* [P,3]                                                      */
-    float* dL_dtransMat;  /* [P,9]                                                      */
+    float* dL_dtransMat;  /* [P,9]  or NULL when not wanted                              */
     float* dL_dsh;        /* [P,M,3]                                                    */
     float* dL_dscales;    /* [P,2]                                                      */
     float* dL_drotations; /* [P,4]                                                      */
@@ -261,7 +261,8 @@ typedef struct MrgsShadeArgs {
     float* dL_dbase_color;         /* [3,H,W]                                              */
     float* dL_dfeatures;           /* [>=5,H,W]: planes 0..4 written                       */
     float* dL_dallmap;             /* [7,H,W]:   planes 1..4 written                       */
-    float* dL_dlevels[MRGS_MAX_MIP_LEVELS]; /* accumulated with atomics; zero them first  */
+    float* dL_dlevels[MRGS_MAX_MIP_LEVELS]; /* float [6][res>>l][res>>l][4] (rgb + pad, 16-byte texels for
+                                               vector atomics); accumulated, zero them first  */
 } MrgsShadeArgs;
 
 MRGS_API int mrgs_shade_forward(const MrgsShadeArgs* args, void* stream);

@@ -145,8 +145,21 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
     unsigned clamped_bits = 0;
     float rgb[3];
     if (p.colors_precomp == nullptr) {
-        sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, pos, {p.campos[0], p.campos[1], p.campos[2]},
-                  rgb, clamped_bits);
+        const Vec3 cam = {p.campos[0], p.campos[1], p.campos[2]};
+        if (p.M == 16) {  // 192-byte rows as 12 float4 loads, coefficients stay in registers
+            float sh_l[48];
+            const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)idx * 48);
+            const int nq = (p.D >= 3) ? 12 : (p.D == 2) ? 7 : (p.D == 1) ? 3 : 1;
+#pragma unroll
+            for (int q = 0; q < 12; ++q) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < nq) v = __ldg(src + q);
+                sh_l[4 * q] = v.x; sh_l[4 * q + 1] = v.y; sh_l[4 * q + 2] = v.z; sh_l[4 * q + 3] = v.w;
+            }
+            sh_to_rgb(p.D, sh_l, pos, cam, rgb, clamped_bits);
+        } else {
+            sh_to_rgb(p.D, p.shs + (size_t)idx * p.M * 3, pos, cam, rgb, clamped_bits);
+        }
     } else {
         rgb[0] = p.colors_precomp[3 * idx];
         rgb[1] = p.colors_precomp[3 * idx + 1];

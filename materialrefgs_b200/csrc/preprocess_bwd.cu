@@ -31,10 +31,24 @@ __device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y 
 
 // Gradient of the SH colour w.r.t. the coefficients (written to dsh, M triples) and w.r.t. the
 // surfel position (returned). g = dL/dRGB with clamped channels already zeroed.
-__device__ V3 sh_backward(int deg, int M, const float* __restrict__ sh_raw, V3 pos, V3 cam, V3 g,
-                          float* __restrict__ dsh) {
-    const V3* sh = reinterpret_cast<const V3*>(sh_raw);
-    V3* out = reinterpret_cast<V3*>(dsh);
+struct Sh3View {  // coefficient triples over a flat float array (constant indices stay in registers)
+    const float* p;
+    __device__ __forceinline__ V3 operator[](int k) const { return {p[3 * k], p[3 * k + 1], p[3 * k + 2]}; }
+};
+struct Sh3Out {
+    float* p;
+    struct Ref {
+        float* q;
+        __device__ __forceinline__ void operator=(V3 v) { q[0] = v.x; q[1] = v.y; q[2] = v.z; }
+    };
+    __device__ __forceinline__ Ref operator[](int k) const { return {p + 3 * k}; }
+};
+
+template <bool kZeroTail>
+__device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restrict__ sh_raw, V3 pos, V3 cam, V3 g,
+                                          float* __restrict__ dsh) {
+    const Sh3View sh{sh_raw};
+    const Sh3Out out{dsh};
     const V3 d0 = {pos.x - cam.x, pos.y - cam.y, pos.z - cam.z};
     const float inv_len = 1.0f / sqrtf(dot(d0, d0));
     const float x = d0.x * inv_len, y = d0.y * inv_len, z = d0.z * inv_len;
@@ -86,7 +100,8 @@ __device__ V3 sh_backward(int deg, int M, const float* __restrict__ sh_raw, V3 p
             }
         }
     }
-    for (int k = written; k < M; ++k) out[k] = {0.f, 0.f, 0.f};
+    if (kZeroTail)
+        for (int k = written; k < M; ++k) out[k] = V3{0.f, 0.f, 0.f};
 
     // through dir = d0 / |d0|
     const V3 ddir = {dot(dx, g), dot(dy, g), dot(dz, g)};
@@ -122,10 +137,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
 
     // pass-through outputs
     p.dL_dopacity[idx] = dopa;
+    if (p.dL_dcolors != nullptr) {
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p.dL_dcolors[3 * idx + c] = dcol[c];
-    for (int c = 0; c < p.S; ++c)
-        p.dL_dfeatures[(size_t)idx * p.S + c] = visible ? g[kGradFeature + c] : 0.f;
+        for (int c = 0; c < 3; ++c) p.dL_dcolors[3 * idx + c] = dcol[c];
+    }
+    if ((p.S & 3) == 0) {
+        // arena features start at float 18: not 16-byte aligned, so gather scalars, store vectors
+        for (int c = 0; c < p.S; c += 4) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (visible) v = make_float4(g[kGradFeature + c], g[kGradFeature + c + 1], g[kGradFeature + c + 2], g[kGradFeature + c + 3]);
+            reinterpret_cast<float4*>(p.dL_dfeatures + (size_t)idx * p.S)[c >> 2] = v;
+        }
+    } else {
+        for (int c = 0; c < p.S; ++c)
+            p.dL_dfeatures[(size_t)idx * p.S + c] = visible ? g[kGradFeature + c] : 0.f;
+    }
 
     float dmean3[3] = {0.f, 0.f, 0.f}, dscale[2] = {0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
     float proxy_x = 0.f, proxy_y = 0.f;
@@ -245,7 +271,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     }
 
     // dL_dtransMat: raw accumulation for the scale/rotation path, augmented for precomputed T
-    {
+    if (p.dL_dtransMat != nullptr) {
         const bool precomp = (p.scales == nullptr);
 #pragma unroll
         for (int i = 0; i < 9; ++i)
@@ -260,10 +286,33 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
             const V3 gc = {(cl & 1) ? 0.f : dcol[0], (cl & 2) ? 0.f : dcol[1], (cl & 4) ? 0.f : dcol[2]};
             const V3 pos = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
             const V3 cam = {p.campos[0], p.campos[1], p.campos[2]};
-            const V3 dpos = sh_backward(p.D, p.M, p.shs + (size_t)idx * p.M * 3, pos, cam, gc, dsh);
+            V3 dpos;
+            if (p.M == 16) {
+                // 192-byte rows: move them as 12 float4 each way, keep the 2x48 values in registers
+                float sh_l[48], dsh_l[48];
+                const float4* src = reinterpret_cast<const float4*>(p.shs + (size_t)idx * 48);
+#pragma unroll
+                for (int q = 0; q < 12; ++q) {
+                    const float4 v = __ldg(src + q);
+                    sh_l[4 * q] = v.x; sh_l[4 * q + 1] = v.y; sh_l[4 * q + 2] = v.z; sh_l[4 * q + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < 48; ++k) dsh_l[k] = 0.f;
+                dpos = sh_backward<false>(p.D, 16, sh_l, pos, cam, gc, dsh_l);
+                float4* dst = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+                for (int q = 0; q < 12; ++q)
+                    dst[q] = make_float4(dsh_l[4 * q], dsh_l[4 * q + 1], dsh_l[4 * q + 2], dsh_l[4 * q + 3]);
+            } else {
+                dpos = sh_backward<true>(p.D, p.M, p.shs + (size_t)idx * p.M * 3, pos, cam, gc, dsh);
+            }
             dmean3[0] += dpos.x;
             dmean3[1] += dpos.y;
             dmean3[2] += dpos.z;
+        } else if (p.M == 16) {
+            float4* dst = reinterpret_cast<float4*>(dsh);
+#pragma unroll
+            for (int q = 0; q < 12; ++q) dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         } else {
             for (int k = 0; k < p.M * 3; ++k) dsh[k] = 0.f;
         }
@@ -274,14 +323,10 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     p.dL_dmeans2D[3 * idx + 0] = proxy_x;
     p.dL_dmeans2D[3 * idx + 1] = proxy_y;
     p.dL_dmeans2D[3 * idx + 2] = 0.f;
-    if (p.dL_dscales != nullptr) {
-        p.dL_dscales[2 * idx + 0] = dscale[0];
-        p.dL_dscales[2 * idx + 1] = dscale[1];
-    }
-    if (p.dL_drotations != nullptr) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) p.dL_drotations[4 * idx + k] = drot[k];
-    }
+    if (p.dL_dscales != nullptr)
+        reinterpret_cast<float2*>(p.dL_dscales)[idx] = make_float2(dscale[0], dscale[1]);
+    if (p.dL_drotations != nullptr)
+        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
 }
 
 }  // namespace

@@ -135,7 +135,8 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
 def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales, rotations,
                            scale_modifier, transMat_precomp, viewmatrix, projmatrix, tanfovx,
                            tanfovy, dL_dout_color, dL_dout_feature, dL_dout_others, sh, sh_degree,
-                           campos, geom, num_rendered, binning, image, contrib, debug):
+                           campos, geom, num_rendered, binning, image, contrib, debug, need_colors=True,
+                           need_transmat=True):
     """Equivalent of _C.rasterize_gaussians_backward (rast/rasterize_points.cu:146-252): returns
     (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
     dL_dscales, dL_drotations)."""
@@ -178,8 +179,10 @@ def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales,
     a.radii = _ptr(radii.contiguous())
     a.geom_buffer, a.binning_buffer, a.image_buffer = _ptr(geom), _ptr(binning), _ptr(image)
     a.dL_dout_color, a.dL_dout_feature, a.dL_dout_others = _ptr(gc_), _ptr(gf_), _ptr(go_)
-    a.dL_dmeans2D, a.dL_dcolors, a.dL_dfeatures = _ptr(dL_dmeans2D), _ptr(dL_dcolors), _ptr(dL_dfeatures)
-    a.dL_dopacity, a.dL_dmeans3D, a.dL_dtransMat = _ptr(dL_dopacity), _ptr(dL_dmeans3D), _ptr(dL_dtransMat)
+    a.dL_dmeans2D, a.dL_dfeatures = _ptr(dL_dmeans2D), _ptr(dL_dfeatures)
+    a.dL_dcolors = _ptr(dL_dcolors) if need_colors else None      # NULL = not wanted, not written
+    a.dL_dtransMat = _ptr(dL_dtransMat) if need_transmat else None
+    a.dL_dopacity, a.dL_dmeans3D = _ptr(dL_dopacity), _ptr(dL_dmeans3D)
     a.dL_dsh = _ptr(dL_dsh)
     a.dL_dscales = _ptr(dL_dscales) if has_sr else None
     a.dL_drotations = _ptr(dL_drotations) if has_sr else None
@@ -237,7 +240,12 @@ class _RasterizeGaussians(torch.autograd.Function):
             rs.bg, means3D, radii, colors_precomp, features, scales, rotations, rs.scale_modifier,
             cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color,
             grad_out_feature, grad_depth, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered,
-            binning, image, contrib, rs.debug)
+            binning, image, contrib, rs.debug, need_colors=ctx.needs_input_grad[3],
+            need_transmat=ctx.needs_input_grad[8])
+        if not ctx.needs_input_grad[3]:
+            grad_colors_precomp = None
+        if not ctx.needs_input_grad[8]:
+            grad_cov3Ds_precomp = None
         # one gradient per forward input (the reference returns a surplus trailing None)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_features,
                 grad_opacities, grad_scales, grad_rotations, grad_cov3Ds_precomp, None)

@@ -110,12 +110,21 @@ class _ShadeSurfel(torch.autograd.Function):
         d_base = torch.empty_like(base_color)
         d_feat = torch.zeros_like(features) if features.shape[0] > 5 else torch.empty_like(features)
         d_allmap = torch.zeros_like(allmap)
-        d_levels = [torch.zeros_like(l) for l in levels]
+        # one flat [texels, 4] accumulation buffer for the whole chain (16-byte texels for vector atomics)
+        counts = [l.shape[0] * l.shape[1] * l.shape[2] for l in levels]
+        flat4 = torch.zeros((sum(counts), 4), dtype=torch.float32, device=dev)
         a.dL_dbase_color, a.dL_dfeatures, a.dL_dallmap = d_base.data_ptr(), d_feat.data_ptr(), d_allmap.data_ptr()
-        for i, d in enumerate(d_levels):
-            a.dL_dlevels[i] = d.data_ptr()
+        off = 0
+        for i, n in enumerate(counts):
+            a.dL_dlevels[i] = flat4.data_ptr() + off * 16
+            off += n
         with torch.cuda.device(dev):
             _lib.check(lib.mrgs_shade_backward(C.byref(a), _stream(dev)), "mrgs_shade_backward")
+        flat3 = flat4[:, :3].contiguous()
+        d_levels, off = [], 0
+        for l, n in zip(levels, counts):
+            d_levels.append(flat3[off:off + n].view(l.shape))
+            off += n
         return (d_base, d_feat, d_allmap, None, None, *d_levels)
 
 
