@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 2
+#define MRGS_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -79,12 +79,14 @@ typedef struct MrgsGeomLayout {
     size_t cf;            /* float [P][cf_stride]: rgb(3) features(S) zero padding                       */
     size_t clamped;       /* uint8 [P]: bit c set when SH colour channel c was clamped to 0             */
     size_t tiles_touched; /* uint32[P]                                                                    */
-    size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched                              */
+    size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched IN DEPTH-SORTED surfel order    */
     size_t rect;          /* uint32[P][2]: (min.x | min.y<<16), (max.x | max.y<<16) tile rectangle        */
     size_t depth;         /* float [P]: view-space depth p_view.z (the low 32 key bits)                   */
     size_t bbox;          /* float [P][4]: conservative pixel bounds (xmin,ymin,xmax,ymax) of the region
                              where the surfel's alpha can reach 1/255; used for per-warp culling          */
-    size_t scan_temp;     /* scan scratch                                                                 */
+    size_t sort_keys;     /* uint32[2][P] ping-pong depth keys (depth bits, 0xffffffff = culled)          */
+    size_t sort_vals;     /* uint32[2][P] ping-pong surfel ids; [0] ends up holding the depth order       */
+    size_t scan_temp;     /* radix-pass histograms / scan block sums                                      */
     size_t scan_temp_bytes;
     size_t total;         /* bytes required                                                               */
     int32_t cf_stride;    /* floats per surfel in `cf` (3+S rounded up to a multiple of 4)                */
@@ -98,10 +100,10 @@ typedef struct MrgsImageLayout {
 } MrgsImageLayout;
 
 typedef struct MrgsBinningLayout {
-    size_t point_list;           /* uint32[R] sorted surfel ids            */
-    size_t point_list_unsorted;  /* uint32[R]                              */
-    size_t keys;                 /* uint64[R] sorted  (tile<<32 | depth)   */
-    size_t keys_unsorted;        /* uint64[R]                              */
+    size_t point_list;           /* uint32[R] surfel ids sorted by (tile, depth, id)       */
+    size_t point_list_unsorted;  /* uint32[R] ping-pong scratch                           */
+    size_t keys;                 /* uint16[R] tile id of every sorted instance            */
+    size_t keys_unsorted;        /* uint16[R] ping-pong scratch                           */
     size_t sort_temp;
     size_t sort_temp_bytes;
     size_t total;
@@ -211,7 +213,8 @@ MRGS_API int32_t mrgs_grad_arena_stride(int32_t S);
 #define MRGS_STAGE_SHADE_FWD 8
 #define MRGS_STAGE_SHADE_BWD 9
 #define MRGS_STAGE_CUBEMAP 10
-#define MRGS_STAGE_COUNT 11
+#define MRGS_STAGE_DEPTH_SORT 11
+#define MRGS_STAGE_COUNT 12
 MRGS_API void mrgs_profile_enable(int32_t on);
 MRGS_API void mrgs_profile_reset(void);
 MRGS_API int mrgs_profile_read(double* ms, int64_t* calls, int32_t n);

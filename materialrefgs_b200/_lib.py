@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 2
+MRGS_ABI_VERSION = 3
 MAX_FEATURES = 24
 TILE = 16
 
@@ -21,7 +21,8 @@ alloc_fn = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
 class GeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in (
-        "rec", "cf", "clamped", "tiles_touched", "point_offsets", "rect", "depth", "bbox", "scan_temp",
+        "rec", "cf", "clamped", "tiles_touched", "point_offsets", "rect", "depth", "bbox", "sort_keys", "sort_vals",
+        "scan_temp",
         "scan_temp_bytes", "total")] + [("cf_stride", C.c_int32)]
 
 
@@ -157,7 +158,7 @@ def load() -> C.CDLL:
 
 
 STAGES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "render_fwd", "render_bwd",
-          "preprocess_bwd", "shade_fwd", "shade_bwd", "cubemap")
+          "preprocess_bwd", "shade_fwd", "shade_bwd", "cubemap", "depth_sort")
 
 
 def profile_read() -> dict:

@@ -134,8 +134,10 @@ int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out) {
     out->rect = off;          off = align_up(off + n * sizeof(uint2));
     out->depth = off;         off = align_up(off + n * sizeof(float));
     out->bbox = off;          off = align_up(off + n * sizeof(float4));
+    out->sort_keys = off;     off = align_up(off + 2 * n * sizeof(uint32_t));
+    out->sort_vals = off;     off = align_up(off + 2 * n * sizeof(uint32_t));
     out->scan_temp = off;
-    out->scan_temp_bytes = scan_temp_bytes(P > 0 ? P : 1);
+    out->scan_temp_bytes = sort_hist_bytes(P > 0 ? P : 1) + (size_t)scan_blocks(P > 0 ? P : 1) * sizeof(uint32_t);
     off = align_up(off + out->scan_temp_bytes);
     out->total = off;
     return MRGS_OK;
@@ -163,10 +165,10 @@ int mrgs_binning_layout(int64_t R, MrgsBinningLayout* out) {
     size_t off = 0;
     out->point_list = off;          off = align_up(off + n * sizeof(uint32_t));
     out->point_list_unsorted = off; off = align_up(off + n * sizeof(uint32_t));
-    out->keys = off;                off = align_up(off + n * sizeof(uint64_t));
-    out->keys_unsorted = off;       off = align_up(off + n * sizeof(uint64_t));
+    out->keys = off;                off = align_up(off + n * sizeof(uint16_t));
+    out->keys_unsorted = off;       off = align_up(off + n * sizeof(uint16_t));
     out->sort_temp = off;
-    out->sort_temp_bytes = sort_temp_bytes(R > 0 ? R : 1);
+    out->sort_temp_bytes = sort_hist_bytes(R > 0 ? R : 1);
     off = align_up(off + out->sort_temp_bytes);
     out->total = off;
     return MRGS_OK;
@@ -238,8 +240,8 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
     const int W = a->width, H = a->height;
     const int grid_x = (W + kTileX - 1) / kTileX, grid_y = (H + kTileY - 1) / kTileY;
     const int tiles = grid_x * grid_y;
-    if (grid_x > 0xffff || grid_y > 0xffff) {
-        set_error("mrgs_forward: image too large");
+    if ((long long)grid_x * grid_y > 0xffff) {
+        set_error("mrgs_forward: %d x %d tiles exceed the 16-bit tile id (max 65535 tiles)", grid_x, grid_y);
         return MRGS_ERR_UNSUPPORTED;
     }
 
@@ -290,7 +292,14 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         pp.rect = (uint2*)(geom + gl.rect);
         pp.depth = (float*)(geom + gl.depth);
         pp.bbox = (float4*)(geom + gl.bbox);
+        pp.sort_key = (uint32_t*)(geom + gl.sort_keys);
         uint32_t* offsets = (uint32_t*)(geom + gl.point_offsets);
+        uint32_t* sort_keys_a = pp.sort_key;
+        uint32_t* sort_keys_b = sort_keys_a + a->P;
+        uint32_t* sort_vals_a = (uint32_t*)(geom + gl.sort_vals);
+        uint32_t* sort_vals_b = sort_vals_a + a->P;
+        uint32_t* hist = (uint32_t*)(geom + gl.scan_temp);
+        uint32_t* block_sums = (uint32_t*)(geom + gl.scan_temp + sort_hist_bytes(a->P));
 
         {
             StageScope sc(MRGS_STAGE_PREPROCESS_FWD, stream, 1);
@@ -298,13 +307,19 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         }
         MRGS_LAUNCH_OK("preprocess_fwd", stream, debug);
 
-        int st;
+        // depth order of the surfels, then instance offsets in that order
+        uint32_t* order = nullptr;
         {
-            StageScope sc(MRGS_STAGE_SCAN, stream, 0);
-            st = run_inclusive_scan(pp.tiles_touched, offsets, a->P, geom + gl.scan_temp,
-                                    gl.scan_temp_bytes, stream);
+            int launches = 0;
+            StageScope sc(MRGS_STAGE_DEPTH_SORT, stream, 0);
+            depth_sort(sort_keys_a, sort_keys_b, sort_vals_a, sort_vals_b, a->P, hist, stream, &order, &launches);
+            g_prof.launches += launches;
         }
-        if (st != MRGS_OK) return st;
+        MRGS_LAUNCH_OK("depth_sort", stream, debug);
+        {
+            StageScope sc(MRGS_STAGE_SCAN, stream, 3);
+            offsets_in_order(order, pp.tiles_touched, a->P, block_sums, offsets, stream);
+        }
         MRGS_LAUNCH_OK("scan", stream, debug);
 
         // R has to reach the host to size the binning buffer (same point as
@@ -336,34 +351,41 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
                 return MRGS_ERR_WORKSPACE;
             }
             a->binning_buffer = bin;
-            uint64_t* keys_unsorted = (uint64_t*)(bin + bl.keys_unsorted);
-            uint64_t* keys = (uint64_t*)(bin + bl.keys);
-            uint32_t* vals_unsorted = (uint32_t*)(bin + bl.point_list_unsorted);
-            uint32_t* vals = (uint32_t*)(bin + bl.point_list);
+            uint16_t* keys_a = (uint16_t*)(bin + bl.keys);
+            uint16_t* keys_b = (uint16_t*)(bin + bl.keys_unsorted);
+            uint32_t* vals_a = (uint32_t*)(bin + bl.point_list);
+            uint32_t* vals_b = (uint32_t*)(bin + bl.point_list_unsorted);
 
             {
                 StageScope sc(MRGS_STAGE_DUPLICATE, stream, 1);
-                launch_duplicate_with_keys(a->P, pp.depth, pp.rect, a->radii, offsets, keys_unsorted,
-                                           vals_unsorted, grid_x, stream);
+                launch_emit_instances(a->P, order, pp.tiles_touched, pp.rect, offsets, keys_a, vals_a, grid_x, stream);
             }
-            MRGS_LAUNCH_OK("duplicate_with_keys", stream, debug);
+            MRGS_LAUNCH_OK("emit_instances", stream, debug);
 
-            const int end_bit = 32 + (int)higher_msb((uint32_t)tiles);
+            // two stable passes over the tile bits only; an even pass count leaves the result in A
+            const int tile_bits = (int)higher_msb((uint32_t)tiles);
+            uint16_t* keys_sorted = nullptr;
+            uint32_t* vals_sorted = nullptr;
             {
+                int launches = 0;
                 StageScope sc(MRGS_STAGE_SORT, stream, 0);
-                st = run_sort_pairs(keys_unsorted, keys, vals_unsorted, vals, R, end_bit,
-                                    bin + bl.sort_temp, bl.sort_temp_bytes, stream);
+                tile_sort(keys_a, keys_b, vals_a, vals_b, R, tile_bits < 9 ? 9 : tile_bits, (uint32_t*)(bin + bl.sort_temp),
+                          stream, &keys_sorted, &vals_sorted, &launches);
+                g_prof.launches += launches;
             }
-            if (st != MRGS_OK) return st;
-            MRGS_LAUNCH_OK("sort_pairs", stream, debug);
+            MRGS_LAUNCH_OK("tile_sort", stream, debug);
+            if (vals_sorted != vals_a) {
+                set_error("mrgs_forward: internal error, tile sort result not in buffer A");
+                return MRGS_ERR_CUDA;
+            }
 
             {
                 StageScope sc(MRGS_STAGE_RANGES, stream, 1);
-                launch_identify_tile_ranges(R, keys, ranges, stream);
+                launch_identify_tile_ranges(R, keys_sorted, ranges, stream);
             }
             MRGS_LAUNCH_OK("identify_tile_ranges", stream, debug);
 
-            rp.point_list = vals;
+            rp.point_list = vals_sorted;
         }
         rp.rec = pp.rec;
         rp.cf = pp.cf;

@@ -1,12 +1,22 @@
-// binning.cu — surfel x tile instance generation, (tile | depth) ordering, per-tile ranges.
+// binning.cu — surfel x tile instance generation and (tile | depth) ordering, all hand-written.
 //
-// Behavioural reference: duplicateWithKeys rasterizer_impl.cu:72-113, the SortPairs call
-// :309-314 with getHigherMsb :37-52, identifyTileRanges :118-140 and the InclusiveSum :283.
-// Required result (bit-exact): instances ordered by (tile id, depth bits) with ties kept in
-// emission order, i.e. ascending surfel id, then row-major tile order of one surfel.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
+// Behavioural reference: duplicateWithKeys rasterizer_impl.cu:72-113, the 64-bit
+// cub::DeviceRadixSort::SortPairs :309-314 (+ getHigherMsb :37-52), identifyTileRanges :118-140 and
+// the InclusiveSum :283. Required result (bit-exact): instances ordered by (tile id, depth bits)
+// with ties kept in emission order, i.e. ascending surfel id.
+//
+// Own design. The reference sorts R instances on 44-45 key bits (6 onesweep passes over 12-byte
+// pairs). The same order is produced here with far less traffic by splitting the key:
+//   1. sort the P surfels ONCE by their 32 depth bits (culled surfels get key 0xffffffff); LSD radix,
+//      stable, input in ascending id order  =>  order by (depth, id);
+//   2. prefix-sum tiles_touched in that order, emit every surfel's (tile, id) instances in that order;
+//   3. stable LSD radix sort of the R instances on the 12-13 tile-id bits only (2 passes, 16-bit keys)
+//      =>  order by (tile, depth, id), identical to the reference's 64-bit sort;
+//   4. tile ranges from the sorted 16-bit keys.
+// One radix pass = per-block digit histogram (+ global digit totals) -> one CTA per digit row turns the
+// counts into global offsets -> stable scatter in which each warp owns a contiguous run of the block's
+// chunk, ranks its items with ballot-built peer masks + running per-(warp, digit) counters (no atomics
+// in the ranking), stages them in digit order in shared memory and writes coalesced runs.
 #include "kernels.cuh"
 
 namespace mrgs {
@@ -25,65 +35,405 @@ uint32_t higher_msb(uint32_t n) {
     return msb;
 }
 
-size_t scan_temp_bytes(int P) {
-    size_t bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
-    return bytes;
-}
-
-size_t sort_temp_bytes(int64_t R) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint64_t*)nullptr, (uint64_t*)nullptr,
-                                    (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)R);
-    return bytes;
-}
-
-int run_inclusive_scan(const uint32_t* in, uint32_t* out, int P, void* temp, size_t temp_bytes,
-                       cudaStream_t stream) {
-    MRGS_CUDA_OK(cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, P, stream));
-    return MRGS_OK;
-}
-
-int run_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
-                   uint32_t* vals_out, int R, int end_bit, void* temp, size_t temp_bytes,
-                   cudaStream_t stream) {
-    MRGS_CUDA_OK(cub::DeviceRadixSort::SortPairs(temp, temp_bytes, keys_in, keys_out, vals_in,
-                                                 vals_out, R, 0, end_bit, stream));
-    return MRGS_OK;
-}
-
 namespace {
 
-__global__ void __launch_bounds__(256)
-duplicate_with_keys_kernel(int P, const float* __restrict__ depth, const uint2* __restrict__ rect,
-                           const int* __restrict__ radii, const uint32_t* __restrict__ offsets,
-                           uint64_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= P) return;
-    if (radii[idx] <= 0) return;
-    uint32_t off = (idx == 0) ? 0u : offsets[idx - 1];
-    const uint2 r = rect[idx];
-    const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff, y1 = r.y >> 16;
-    const uint32_t depth_bits = __float_as_uint(depth[idx]);
-    for (int y = y0; y < y1; ++y) {
-        for (int x = x0; x < x1; ++x) {
-            const uint64_t key = ((uint64_t)(uint32_t)(y * grid_x + x) << 32) | depth_bits;
-            keys[off] = key;
-            values[off] = (uint32_t)idx;
-            ++off;
+constexpr unsigned kFullMask = 0xffffffffu;
+constexpr int kSortThreads = 256;
+constexpr int kSortWarps = kSortThreads / 32;
+constexpr int kItemsPerThread = 16;
+constexpr int kChunk = kSortThreads * kItemsPerThread;  // 4096 items per block
+constexpr int kWarpRun = 32 * kItemsPerThread;          // 512 consecutive items per warp
+constexpr int kMaxBins = 256;
+
+// Lanes of the warp holding the same digit (match.any semantics, but built from one ballot per digit
+// bit: the MATCH instruction itself is an order of magnitude slower than 8 VOTE + 8 LOP3).
+__device__ __forceinline__ unsigned warp_peers(uint32_t d, int bits, bool valid) {
+    unsigned peers = __ballot_sync(kFullMask, valid);
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+        if (b < bits) {
+            const bool bit = (d >> b) & 1u;
+            const unsigned v = __ballot_sync(kFullMask, bit);
+            peers &= bit ? v : ~v;
         }
+    }
+    return peers;
+}
+
+// per-block digit counts [digit][block] and global digit totals
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+radix_hist_kernel(const KeyT* __restrict__ keys, int n, int shift, int bits, uint32_t* __restrict__ block_hist,
+                  uint32_t* __restrict__ digit_total, int num_blocks) {
+    __shared__ uint32_t s_hist[kMaxBins];
+    const int bins = 1 << bits;
+    for (int i = threadIdx.x; i < bins; i += kSortThreads) s_hist[i] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kChunk;
+    const uint32_t mask = (uint32_t)bins - 1;
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll 4
+    for (int k = 0; k < kItemsPerThread; ++k) {
+        const int i = base + k * kSortThreads + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t d = valid ? (((uint32_t)keys[i] >> shift) & mask) : 0u;
+        // neighbouring instances share digits: one shared atomic per distinct digit of the warp
+        const unsigned peers = warp_peers(d, bits, valid);
+        if (valid && (peers & lt) == 0) atomicAdd(&s_hist[d], (uint32_t)__popc(peers));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < bins; i += kSortThreads) {
+        const uint32_t c = s_hist[i];
+        block_hist[(size_t)i * num_blocks + blockIdx.x] = c;
+        if (c) atomicAdd(&digit_total[i], c);
+    }
+}
+
+// one CTA per digit row: block_hist[d][*] -> exclusive prefix over blocks + start of digit d
+__global__ void __launch_bounds__(256)
+radix_row_scan_kernel(uint32_t* __restrict__ block_hist, const uint32_t* __restrict__ digit_total, int bins,
+                      int num_blocks) {
+    __shared__ uint32_t s_warp[8];
+    __shared__ uint32_t s_start;
+    const int d = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // start of this digit = sum of the totals of all smaller digits (bins <= 256: one value per thread)
+    {
+        uint32_t v = (threadIdx.x < d && threadIdx.x < bins) ? digit_total[threadIdx.x] : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+        if (lane == 0) s_warp[warp] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t t = 0;
+#pragma unroll
+            for (int w = 0; w < 8; ++w) t += s_warp[w];
+            s_start = t;
+        }
+        __syncthreads();
+    }
+    uint32_t* row = block_hist + (size_t)d * num_blocks;
+    uint32_t carry = s_start;
+    for (int base = 0; base < num_blocks; base += 256 * 4) {
+        const int i0 = base + threadIdx.x * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) v[k] = (i0 + k < num_blocks) ? row[i0 + k] : 0u;
+        const uint32_t mine = v[0] + v[1] + v[2] + v[3];
+        uint32_t incl = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        __syncthreads();  // s_warp reuse
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) {
+            const uint32_t c = s_warp[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        uint32_t run = carry + before + incl - mine;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i0 + k < num_blocks) row[i0 + k] = run;
+            run += v[k];
+        }
+        carry += total;
+    }
+}
+
+// exclusive scan of `n` uint32 in place by ONE CTA (used for the few hundred scan block sums)
+__global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restrict__ data, int n) {
+    __shared__ uint32_t s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int seg = (n + 1023) / 1024;
+    const int lo = min(n, (int)threadIdx.x * seg), hi = min(n, lo + seg);
+    uint32_t mine = 0;
+    for (int i = lo; i < hi; ++i) mine += data[i];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, w, d);
+            if (lane >= d) w += t;
+        }
+        s_warp[lane] = w;  // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = (warp ? s_warp[warp - 1] : 0u) + (incl - mine);
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t v = data[i];
+        data[i] = run;
+        run += v;
+    }
+}
+
+// Stable scatter of one radix pass. Item order inside a block: warp w owns items
+// [w*512, (w+1)*512) of the chunk, walked 32 at a time, so (warp, step, lane) is ascending item index.
+// Items are first placed at their block-local sorted position in shared memory, then written out so
+// that every digit's run leaves as contiguous, coalesced stores.
+template <typename KeyT, bool IOTA>
+__global__ void __launch_bounds__(kSortThreads, 3)
+radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
+                     KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
+                     const uint32_t* __restrict__ block_off, int num_blocks) {
+    const int bins = 1 << bits;
+    __shared__ uint32_t s_cnt[kSortWarps][kMaxBins];  // per-warp digit counts -> local rank bases
+    __shared__ uint32_t s_lstart[kMaxBins];           // block-local start of every digit
+    __shared__ uint32_t s_gbase[kMaxBins];            // global start of this block's run of every digit
+    __shared__ uint32_t s_wsum[kSortWarps];
+    __shared__ KeyT s_keys[kChunk];
+    __shared__ uint32_t s_vals[kChunk];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSortWarps * kMaxBins; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    const uint32_t mask = (uint32_t)bins - 1;
+    const int bbase = blockIdx.x * kChunk;
+    const int wbase = bbase + warp * kWarpRun;
+    KeyT key[kItemsPerThread];
+    const unsigned lt = (1u << lane) - 1u;
+
+    // phase 1: per-warp digit counts (keys stay in registers)
+#pragma unroll
+    for (int k = 0; k < kItemsPerThread; ++k) {
+        const int i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        key[k] = valid ? keys_in[i] : (KeyT)0;
+        const uint32_t d = ((uint32_t)key[k] >> shift) & mask;
+        const unsigned peers = warp_peers(d, bits, valid);
+        if (valid && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // phase 2: block-local exclusive scan over digits (bins <= 256 = one digit per thread), then the
+    // per-warp bases inside each digit's local run
+    {
+        uint32_t tot = 0;
+        const int d = threadIdx.x;
+        if (d < bins) {
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) tot += s_cnt[w][d];
+        }
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint32_t before = 0;
+#pragma unroll
+        for (int w = 0; w < kSortWarps; ++w)
+            if (w < warp) before += s_wsum[w];
+        if (d < bins) {
+            uint32_t run = before + incl - tot;
+            s_lstart[d] = run;
+            s_gbase[d] = block_off[(size_t)d * num_blocks + blockIdx.x];
+#pragma unroll
+            for (int w = 0; w < kSortWarps; ++w) {
+                const uint32_t c = s_cnt[w][d];
+                s_cnt[w][d] = run;
+                run += c;
+            }
+        }
+    }
+    __syncthreads();
+    // phase 3: rank, place at the block-local sorted position
+#pragma unroll
+    for (int k = 0; k < kItemsPerThread; ++k) {
+        const int i = wbase + k * 32 + lane;
+        const bool valid = i < n;
+        const uint32_t d = ((uint32_t)key[k] >> shift) & mask;
+        const unsigned peers = warp_peers(d, bits, valid);
+        uint32_t pos = 0;
+        if (valid) pos = s_cnt[warp][d] + __popc(peers & lt);
+        __syncwarp();
+        if (valid && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
+        __syncwarp();
+        if (valid) {
+            s_keys[pos] = key[k];
+            s_vals[pos] = IOTA ? (uint32_t)i : vals_in[i];
+        }
+    }
+    __syncthreads();
+    // phase 4: coalesced write-out, local position -> global position of the same digit run
+    const int count = min(kChunk, n - bbase);
+    for (int pos = threadIdx.x; pos < count; pos += kSortThreads) {
+        const KeyT kk = s_keys[pos];
+        const uint32_t d = ((uint32_t)kk >> shift) & mask;
+        const uint32_t g = s_gbase[d] + ((uint32_t)pos - s_lstart[d]);
+        keys_out[g] = kk;
+        vals_out[g] = s_vals[pos];
+    }
+}
+
+template <typename KeyT>
+int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, int n, int total_bits,
+                     bool first_pass_iota, uint32_t* block_hist, cudaStream_t stream, KeyT** keys_final,
+                     uint32_t** vals_final) {
+    // as few passes of <= 8 bits as possible, evenly split; block_hist = [256][blocks] counts followed
+    // by [passes][256] digit totals
+    const int passes = (total_bits + 7) / 8;
+    const int num_blocks = (n + kChunk - 1) / kChunk;
+    uint32_t* totals = block_hist + (size_t)kMaxBins * num_blocks;
+    cudaMemsetAsync(totals, 0, (size_t)passes * kMaxBins * sizeof(uint32_t), stream);
+    KeyT* kin = keys_a;
+    KeyT* kout = keys_b;
+    uint32_t* vin = vals_a;
+    uint32_t* vout = vals_b;
+    int shift = 0;
+    for (int pass = 0; pass < passes; ++pass) {
+        const int bits = (total_bits - shift + (passes - pass) - 1) / (passes - pass);
+        const int bins = 1 << bits;
+        uint32_t* tot = totals + (size_t)pass * kMaxBins;
+        radix_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, shift, bits, block_hist, tot, num_blocks);
+        radix_row_scan_kernel<<<bins, 256, 0, stream>>>(block_hist, tot, bins, num_blocks);
+        if (pass == 0 && first_pass_iota)
+            radix_scatter_kernel<KeyT, true><<<num_blocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, bits,
+                                                                                    block_hist, num_blocks);
+        else
+            radix_scatter_kernel<KeyT, false><<<num_blocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, bits,
+                                                                                     block_hist, num_blocks);
+        KeyT* tk = kin; kin = kout; kout = tk;
+        uint32_t* tv = vin; vin = vout; vout = tv;
+        shift += bits;
+    }
+    *keys_final = kin;
+    *vals_final = vin;
+    return passes * 3;
+}
+
+// inclusive scan of tiles_touched gathered through the depth-sorted surfel order -------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan_256(uint32_t mine, uint32_t* s_warp, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) before += c;
+        sum += c;
+    }
+    total = sum;
+    return before + incl - mine;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+gather_reduce_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched, int n,
+                     uint32_t* __restrict__ block_sums) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k)
+        if (base + k < n) mine += tiles_touched[order[base + k]];
+    uint32_t total;
+    block_exclusive_scan_256(mine, s_warp, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kScanThreads)
+gather_scan_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched, int n,
+                   const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ offsets_incl) {
+    __shared__ uint32_t s_warp[kScanThreads / 32];
+    const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
+    uint32_t v[kScanItems];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        v[k] = (base + k < n) ? tiles_touched[order[base + k]] : 0u;
+        mine += v[k];
+    }
+    uint32_t total;
+    uint32_t run = block_offsets[blockIdx.x] + block_exclusive_scan_256(mine, s_warp, total);
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) {
+        run += v[k];
+        if (base + k < n) offsets_incl[base + k] = run;
+    }
+}
+
+// A warp expands 32 consecutive surfels of the depth order. Their instances form ONE contiguous
+// output segment, so lanes stride over output positions (coalesced 2-byte / 4-byte stores) and find the
+// owning surfel with a 5-step binary search over the warp's 32 inclusive offsets.
+__global__ void __launch_bounds__(256)
+emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
+                      const uint2* __restrict__ rect, const uint32_t* __restrict__ offsets_incl,
+                      uint16_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x) {
+    __shared__ uint32_t s_end[8][32];
+    __shared__ uint32_t s_id[8][32];
+    __shared__ uint2 s_rect[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = (blockIdx.x * 8 + warp) * 32;
+    if (k0 >= P) return;
+    const int k = k0 + lane;
+    const uint32_t seg_begin = (k0 == 0) ? 0u : offsets_incl[k0 - 1];
+    uint32_t end = seg_begin;
+    uint32_t id = 0;
+    if (k < P) {
+        end = offsets_incl[k];
+        id = order[k];
+    }
+    const int n_valid = min(32, P - k0);
+    const uint32_t seg_end = __shfl_sync(kFullMask, end, n_valid - 1);
+    if (k >= P) end = seg_end;  // lanes past the last surfel own an empty range at the segment end
+    const uint32_t prev_end = __shfl_up_sync(kFullMask, end, 1);
+    const uint32_t begin_mine = lane ? prev_end : seg_begin;
+    s_end[warp][lane] = end;
+    s_id[warp][lane] = id;
+    if (k < P && end > begin_mine) s_rect[warp][lane] = rect[id];
+    __syncwarp();
+    for (uint32_t pos = seg_begin + lane; pos < seg_end; pos += 32) {
+        // first lane j with s_end[j] > pos
+        int lo = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1)
+            if (s_end[warp][lo + step - 1] <= pos) lo += step;
+        const uint32_t start_j = lo ? s_end[warp][lo - 1] : seg_begin;
+        const uint2 r = s_rect[warp][lo];
+        const int x0 = r.x & 0xffff, y0 = r.x >> 16, x1 = r.y & 0xffff;
+        const int w = x1 - x0;
+        const int t = (int)(pos - start_j);
+        const int ty = t / w, tx = t - ty * w;
+        keys[pos] = (uint16_t)((y0 + ty) * grid_x + x0 + tx);
+        values[pos] = s_id[warp][lo];
     }
 }
 
 __global__ void __launch_bounds__(256)
-identify_tile_ranges_kernel(int R, const uint64_t* __restrict__ keys, uint2* __restrict__ ranges) {
+identify_tile_ranges_kernel(int R, const uint16_t* __restrict__ keys, uint2* __restrict__ ranges) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
-    const uint32_t tile = (uint32_t)(keys[idx] >> 32);
+    const uint32_t tile = keys[idx];
     if (idx == 0) {
         ranges[tile].x = 0;
     } else {
-        const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+        const uint32_t prev = keys[idx - 1];
         if (tile != prev) {
             ranges[prev].y = idx;
             ranges[tile].x = idx;
@@ -94,14 +444,43 @@ identify_tile_ranges_kernel(int R, const uint64_t* __restrict__ keys, uint2* __r
 
 }  // namespace
 
-void launch_duplicate_with_keys(int P, const float* depth, const uint2* rect, const int* radii,
-                                const uint32_t* offsets, uint64_t* keys, uint32_t* values,
-                                int grid_x, cudaStream_t stream) {
-    duplicate_with_keys_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, depth, rect, radii, offsets,
-                                                                    keys, values, grid_x);
+int sort_blocks(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
+size_t sort_hist_bytes(int64_t n) {
+    return ((size_t)kMaxBins * (size_t)(sort_blocks(n) > 0 ? sort_blocks(n) : 1) + 4 * kMaxBins) * sizeof(uint32_t);
+}
+int scan_blocks(int n) { return (n + kScanChunk - 1) / kScanChunk; }
+
+int depth_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int P, uint32_t* block_hist,
+               cudaStream_t stream, uint32_t** order, int* launches) {
+    uint32_t* kf;
+    *launches = radix_sort_pairs<uint32_t>(keys_a, keys_b, vals_a, vals_b, P, 32, true, block_hist, stream, &kf, order);
+    return MRGS_OK;
 }
 
-void launch_identify_tile_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream) {
+int offsets_in_order(const uint32_t* order, const uint32_t* tiles_touched, int P, uint32_t* block_sums,
+                     uint32_t* offsets_incl, cudaStream_t stream) {
+    const int nb = scan_blocks(P);
+    gather_reduce_kernel<<<nb, kScanThreads, 0, stream>>>(order, tiles_touched, P, block_sums);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, nb);
+    gather_scan_kernel<<<nb, kScanThreads, 0, stream>>>(order, tiles_touched, P, block_sums, offsets_incl);
+    return MRGS_OK;
+}
+
+void launch_emit_instances(int P, const uint32_t* order, const uint32_t* tiles_touched, const uint2* rect,
+                           const uint32_t* offsets_incl, uint16_t* keys, uint32_t* values, int grid_x,
+                           cudaStream_t stream) {
+    emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, tiles_touched, rect, offsets_incl, keys, values,
+                                                              grid_x);
+}
+
+int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int R, int tile_bits,
+              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches) {
+    *launches = radix_sort_pairs<uint16_t>(keys_a, keys_b, vals_a, vals_b, R, tile_bits, false, block_hist, stream,
+                                           keys_sorted, vals_sorted);
+    return MRGS_OK;
+}
+
+void launch_identify_tile_ranges(int R, const uint16_t* keys, uint2* ranges, cudaStream_t stream) {
     identify_tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, keys, ranges);
 }
 

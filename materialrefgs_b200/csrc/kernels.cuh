@@ -30,25 +30,30 @@ struct PreprocessParams {
     uint2* rect;
     float* depth;
     float4* bbox;
+    uint32_t* sort_key;  // depth bits, 0xffffffff for culled surfels
 };
 
 void launch_preprocess_fwd(const PreprocessParams& p, cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* viewmatrix, uint8_t* present,
                          cudaStream_t stream);
 
-// ---- binning -------------------------------------------------------------------------------
-size_t scan_temp_bytes(int P);
-size_t sort_temp_bytes(int64_t R);
-int run_inclusive_scan(const uint32_t* in, uint32_t* out, int P, void* temp, size_t temp_bytes,
-                       cudaStream_t stream);
-void launch_duplicate_with_keys(int P, const float* depth, const uint2* rect, const int* radii,
-                                const uint32_t* offsets, uint64_t* keys, uint32_t* values,
-                                int grid_x, cudaStream_t stream);
-int run_sort_pairs(const uint64_t* keys_in, uint64_t* keys_out, const uint32_t* vals_in,
-                   uint32_t* vals_out, int R, int end_bit, void* temp, size_t temp_bytes,
-                   cudaStream_t stream);
-void launch_identify_tile_ranges(int R, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+// ---- binning (all hand-written, see binning.cu) ------------------------------------------------
 uint32_t higher_msb(uint32_t n);
+int sort_blocks(int64_t n);
+size_t sort_hist_bytes(int64_t n);
+int scan_blocks(int n);
+// depth-sorts the P surfels (keys_a holds the 32-bit keys, values are implicit ids); *order = sorted ids
+int depth_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int P, uint32_t* block_hist,
+               cudaStream_t stream, uint32_t** order, int* launches);
+// offsets_incl[k] = inclusive prefix sum of tiles_touched[order[k]]
+int offsets_in_order(const uint32_t* order, const uint32_t* tiles_touched, int P, uint32_t* block_sums,
+                     uint32_t* offsets_incl, cudaStream_t stream);
+void launch_emit_instances(int P, const uint32_t* order, const uint32_t* tiles_touched, const uint2* rect,
+                           const uint32_t* offsets_incl, uint16_t* keys, uint32_t* values, int grid_x,
+                           cudaStream_t stream);
+int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int R, int tile_bits,
+              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches);
+void launch_identify_tile_ranges(int R, const uint16_t* keys, uint2* ranges, cudaStream_t stream);
 
 // ---- tile blend ----------------------------------------------------------------------------
 struct RenderFwdParams {

@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
 
     p.radii[idx] = 0;
     p.tiles_touched[idx] = 0;
+    p.sort_key[idx] = 0xffffffffu;
 
     const Vec3 pos = {p.means3D[3 * idx], p.means3D[3 * idx + 1], p.means3D[3 * idx + 2]};
     const Vec3 pv = view_point(p.viewmatrix, pos);
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
     rec[2] = make_float4(T[8], cx, cy, opacity);
     rec[3] = make_float4(normal.x, normal.y, normal.z, tau);
     p.depth[idx] = pv.z;
+    p.sort_key[idx] = __float_as_uint(pv.z);
     p.bbox[idx] = bb;
 
     p.rect[idx] = make_uint2((unsigned)x0 | ((unsigned)y0 << 16), (unsigned)x1 | ((unsigned)y1 << 16));

@@ -116,12 +116,17 @@ def decode_mrgs_image(img: torch.Tensor, H: int, W: int):
     }
 
 
-def decode_mrgs_binning(binning: torch.Tensor, R: int):
+def decode_mrgs_binning(binning: torch.Tensor, R: int, depths: torch.Tensor = None):
+    """libmrgs keeps the sorted surfel ids and the 16-bit tile id of every sorted instance; the
+    reference's 64-bit key (tile << 32 | depth bits) is rebuilt from them for bit-exact comparison."""
     from materialrefgs_b200 import _lib
     lib = _lib.load()
     bl = _lib.BinningLayout()
     assert lib.mrgs_binning_layout(R, C.byref(bl)) == 0
-    return {
-        "point_list": binning[bl.point_list:bl.point_list + 4 * R].view(torch.int32),
-        "keys": binning[bl.keys:bl.keys + 8 * R].view(torch.int64),
-    }
+    point_list = binning[bl.point_list:bl.point_list + 4 * R].view(torch.int32)
+    tiles = binning[bl.keys:bl.keys + 2 * R].view(torch.int16).to(torch.int64) & 0xffff
+    out = {"point_list": point_list, "tile_ids": tiles}
+    if depths is not None:
+        bits = depths.view(torch.int32)[point_list.long()].to(torch.int64) & 0xffffffff
+        out["keys"] = (tiles << 32) | bits
+    return out

@@ -50,7 +50,7 @@ def test_against_reference_golden(path):
     assert np.array_equal(n(gm["depths"])[v].view(np.uint32), z["depths"][v].view(np.uint32))
     assert np.array_equal(n(gm["means2D"])[v], z["means2D"][v])
     assert np.array_equal(n(gm["transMat"])[v], z["transMat"][v])
-    bm = refimpl.decode_mrgs_binning(binning, R)
+    bm = refimpl.decode_mrgs_binning(binning, R, gm["depths"])
     assert np.array_equal(n(bm["keys"]), z["keys"])
     assert np.array_equal(n(bm["point_list"]), z["point_list"])
     im = refimpl.decode_mrgs_image(img, H, W)
@@ -105,7 +105,9 @@ def test_against_cpu_oracle(P, S, W, H, opacity, seed):
     assert mism <= 1e-3
     if mism == 0:
         assert R == R_cpu
-        bm = refimpl.decode_mrgs_binning(binning, R)
+        gm = refimpl.decode_mrgs_geom(geom, P, S)
+        bm = refimpl.decode_mrgs_binning(binning, R, gm["depths"])
+        assert np.array_equal(bm["keys"].cpu().numpy().view(np.uint64), o.keys)
         assert np.array_equal(bm["point_list"].cpu().numpy().view(np.uint32), o.point_list)
         im = refimpl.decode_mrgs_image(img, H, W)
         assert (im["n_contrib"].cpu().numpy().view(np.uint32) != o.n_contrib[0]).mean() <= 1e-3

@@ -108,7 +108,7 @@ def test_forward_buffers_bit_exact(ref_ext, P, S, W, H, opacity):
     assert not flips.any()
 
     br = refimpl.decode_ref_binning(bin_r, R)
-    bm = refimpl.decode_mrgs_binning(binning, R)
+    bm = refimpl.decode_mrgs_binning(binning, R, gm["depths"])
     assert torch.equal(bm["keys"], br["keys"])
     assert torch.equal(bm["point_list"], br["point_list"])
 
@@ -231,7 +231,7 @@ def test_full_size_properties():
         cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, cloud.shs, 3,
         cam.camera_center, False, False)
     gm = refimpl.decode_mrgs_geom(geom, P, S)
-    bm = refimpl.decode_mrgs_binning(binning, R)
+    bm = refimpl.decode_mrgs_binning(binning, R, gm["depths"])
     im = refimpl.decode_mrgs_image(img, H, W)
     assert int(gm["tiles_touched"].sum()) == R
     keys = bm["keys"]
