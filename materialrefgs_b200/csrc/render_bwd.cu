@@ -9,10 +9,10 @@
 //     evaluated — walks back to front 32 instances per step, culls them against the surfel's
 //     conservative alpha-support box (1/32 of an instruction stream per instance) and stages only
 //     the survivors' records in its private shared-memory slots;
-//   * gradients of one instance are summed across the 32 pixels of a warp with a transposing
-//     butterfly (31 shuffles for up to 32 values, lane l ends up owning value l) and leave the
-//     warp as ONE coalesced red.global.add per instance instead of 16+S same-address atomics
-//     per pixel;
+//   * gradients of one instance are summed across the 32 pixels of a warp by transposing them
+//     through a padded shared-memory tile (one STS per value, then lane c sums row c with 8
+//     conflict-free LDS.128) and leave the warp as ONE coalesced red.global.add per instance
+//     instead of 16+S same-address atomics per pixel;
 //   * a warp skips the reduction when none of its pixels is touched by the instance.
 #include "kernels.cuh"
 #include "splat_math.cuh"
@@ -23,22 +23,13 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
-// v[0..31] (entries >= NV are treated as zero) -> returns sum over the warp of v[lane].
-template <int NV>
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool upper = (lane & half) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const float a = (i < NV) ? v[i] : 0.0f;
-            const float b = (i + half < NV) ? v[i + half] : 0.0f;
-            const float send = upper ? a : b;
-            const float keep = upper ? b : a;
-            v[i] = keep + __shfl_xor_sync(kFull, send, half);
-        }
-    }
-    return v[0];
+constexpr int kRedStride = 36;  // floats per value row: 32 lanes + 4 pad keeps LDS.128 conflict-free
+
+template <int NQ>
+constexpr int bwd_smem_bytes() {
+    // per warp: 4 geometry vectors + NQ colour vectors + ids for 32 staged instances, and the
+    // [NV][36] transposition buffer of the warp reduction
+    return kWarpsPerTile * ((4 + NQ) * 32 * 16 + 32 * 4 + (kGradColor + NQ * 4) * kRedStride * 4);
 }
 
 template <int NQ>
@@ -47,9 +38,12 @@ render_bwd_kernel(const RenderBwdParams p) {
     constexpr int NC = NQ * 4;           // colour + feature (+ padding) channels
     constexpr int NV = kGradColor + NC;  // values per instance incl. padding channels
     constexpr bool kTwoPass = NV > 32;
-    __shared__ float4 s_g[kWarpsPerTile][4][32];
-    __shared__ float4 s_cf[kWarpsPerTile][NQ][32];
-    __shared__ uint32_t s_id[kWarpsPerTile][32];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 (*s_g)[4][32] = reinterpret_cast<float4 (*)[4][32]>(smem_raw);
+    float4 (*s_cf)[NQ][32] = reinterpret_cast<float4 (*)[NQ][32]>(smem_raw + kWarpsPerTile * 4 * 32 * 16);
+    uint32_t (*s_id)[32] = reinterpret_cast<uint32_t (*)[32]>(smem_raw + kWarpsPerTile * (4 + NQ) * 32 * 16);
+    float* s_red = reinterpret_cast<float*>(smem_raw + kWarpsPerTile * ((4 + NQ) * 32 * 16 + 32 * 4)) +
+                   (threadIdx.x >> 5) * (NV * kRedStride);
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -160,18 +154,15 @@ render_bwd_kernel(const RenderBwdParams p) {
             const bool valid = (e < last_contributor) && ray_splat(g0, g1, g2, g3.w, pxf, pyf, h);
             if (!__any_sync(kFull, valid)) continue;
 
-            float v[32];
+            float v[NV];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) v[c] = 0.0f;
-            float vx[kTwoPass ? 32 : 1];  // channels that do not fit the first 32-value pass
-            if constexpr (kTwoPass) {
-#pragma unroll
-                for (int c = 0; c < 32; ++c) vx[c] = 0.0f;
-            }
+            for (int c = 0; c < NV; ++c) v[c] = 0.0f;
 
             if (valid) {
                 const float alpha = h.alpha, G = h.G;
-                T = T / (1.0f - alpha);
+                // gradients tolerate approximate reciprocals (1e-3 bar); every skip decision above is exact
+                const float inv_1ma = __fdividef(1.0f, 1.0f - alpha);
+                T = T * inv_1ma;
                 const float w = alpha * T;
                 float dL_dalpha = 0.0f;
 #pragma unroll
@@ -185,20 +176,13 @@ render_bwd_kernel(const RenderBwdParams p) {
                         last_val[c] = cc[k];
                         dL_dalpha += (cc[k] - accum_rec[c]) * dL_dpix[c];
                         const float gcf = w * dL_dpix[c];
-                        if constexpr (!kTwoPass) {
-                            v[kGradColor + c] = gcf;
-                        } else {
-                            if (kGradColor + c < 32)
-                                v[kGradColor + c] = gcf;
-                            else
-                                vx[(kGradColor + c) & 31] = gcf;
-                        }
+                        v[kGradColor + c] = gcf;
                     }
                 }
 
                 const float c_d = h.depth;
                 const float m_d = distortion_coord(c_d);
-                const float dmd_dd = (kFar * kNear) / ((kFar - kNear) * c_d * c_d);
+                const float dmd_dd = ((kFar * kNear) / (kFar - kNear)) * __fdividef(1.0f, c_d * c_d);
                 float dL_dz = 0.0f;
                 if (e == median_contributor - 1) dL_dz += dL_dmedian;
                 const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
@@ -226,7 +210,7 @@ render_bwd_kernel(const RenderBwdParams p) {
 
                 dL_dalpha *= T;
                 last_alpha = alpha;
-                dL_dalpha += (-T_final / (1.0f - alpha)) * bg_dot_dpixel;
+                if (bg_dot_dpixel != 0.0f) dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                 const float dL_dG = g2.w * dL_dalpha;
                 dL_dz += w * dL_ddepth;
@@ -235,8 +219,9 @@ render_bwd_kernel(const RenderBwdParams p) {
                     const float Twx = g0.w, Twy = g1.w;
                     const float dL_dsx = dL_dG * -G * h.sx + dL_dz * Twx;
                     const float dL_dsy = dL_dG * -G * h.sy + dL_dz * Twy;
-                    const float dsx_pz = dL_dsx / h.pz;
-                    const float dsy_pz = dL_dsy / h.pz;
+                    const float inv_pz = __fdividef(1.0f, h.pz);
+                    const float dsx_pz = dL_dsx * inv_pz;
+                    const float dsy_pz = dL_dsy * inv_pz;
                     const float dpx = dsx_pz, dpy = dsy_pz, dpz = -(dsx_pz * h.sx + dsy_pz * h.sy);
                     // dL_dk = cross(l, dL_dp), dL_dl = cross(dL_dp, k)
                     const float dkx = h.ly * dpz - h.lz * dpy;
@@ -264,14 +249,29 @@ render_bwd_kernel(const RenderBwdParams p) {
                 v[kGradOpacity] = G * dL_dalpha;
             }
 
+            // transpose through shared memory: lane c sums value c over the 32 pixels (8 LDS.128 + 31 FADD)
+            // and the warp leaves ONE coalesced red.global.add per arena row
+#pragma unroll
+            for (int c = 0; c < NV; ++c) s_red[c * kRedStride + lane] = v[c];
+            __syncwarp();
             float* row = p.grad_arena + (size_t)s_id[warp][j] * p.grad_stride;
             const int n_live = kGradFeature + p.S;  // padding channels carry no gradient
-            const float total = warp_transpose_reduce<(NV < 32 ? NV : 32)>(v, lane);
-            if (lane < min(n_live, 32)) atomicAdd(row + lane, total);
-            if constexpr (kTwoPass) {
-                const float total2 = warp_transpose_reduce<NV - 32>(vx, lane);
-                if (32 + lane < n_live) atomicAdd(row + 32 + lane, total2);
+#pragma unroll
+            for (int pass = 0; pass < (kTwoPass ? 2 : 1); ++pass) {
+                const int c = pass * 32 + lane;
+                if (c < n_live) {
+                    const float4* r4 = reinterpret_cast<const float4*>(s_red + c * kRedStride);
+                    float part[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 t = r4[q];
+                        part[q] = (t.x + t.y) + (t.z + t.w);
+                    }
+                    const float total = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+                    atomicAdd(row + c, total);
+                }
             }
+            __syncwarp();
         }
         __syncwarp();  // all lanes are past their reads before the slots are overwritten
     }
@@ -282,10 +282,17 @@ render_bwd_kernel(const RenderBwdParams p) {
 int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream) {
     const dim3 grid(p.grid_x, p.grid_y);
     switch (p.cf_stride / 4) {
-#define MRGS_CASE(NQ)                                                   \
-    case NQ:                                                            \
-        render_bwd_kernel<NQ><<<grid, kTilePixels, 0, stream>>>(p);     \
-        break;
+#define MRGS_CASE(NQ)                                                                              \
+    case NQ: {                                                                                     \
+        static bool configured = false;                                                            \
+        if (!configured) {                                                                         \
+            cudaFuncSetAttribute(render_bwd_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                 bwd_smem_bytes<NQ>());                                            \
+            configured = true;                                                                     \
+        }                                                                                          \
+        render_bwd_kernel<NQ><<<grid, kTilePixels, bwd_smem_bytes<NQ>(), stream>>>(p);             \
+        break;                                                                                     \
+    }
         MRGS_CASE(1)
         MRGS_CASE(2)
         MRGS_CASE(3)
