@@ -49,17 +49,19 @@ struct Profiler {
 };
 static Profiler g_prof;
 
-static void prof_collect() {
-    for (int s = 0; s < MRGS_STAGE_COUNT; ++s) {
-        if (!g_prof.pending[s]) continue;
-        float t = 0.f;
-        if (cudaEventSynchronize(g_prof.ev[s][1]) == cudaSuccess &&
-            cudaEventElapsedTime(&t, g_prof.ev[s][0], g_prof.ev[s][1]) == cudaSuccess) {
-            g_prof.ms[s] += t;
-            g_prof.calls[s] += 1;
-        }
-        g_prof.pending[s] = false;
+static void prof_collect_one(int s) {
+    if (!g_prof.pending[s]) return;
+    float t = 0.f;
+    if (cudaEventSynchronize(g_prof.ev[s][1]) == cudaSuccess &&
+        cudaEventElapsedTime(&t, g_prof.ev[s][0], g_prof.ev[s][1]) == cudaSuccess) {
+        g_prof.ms[s] += t;
+        g_prof.calls[s] += 1;
     }
+    g_prof.pending[s] = false;
+}
+
+static void prof_collect() {
+    for (int s = 0; s < MRGS_STAGE_COUNT; ++s) prof_collect_one(s);
 }
 
 struct StageScope {
@@ -75,7 +77,9 @@ struct StageScope {
             }
             g_prof.created = true;
         }
-        if (g_prof.pending[stage]) prof_collect();  // one in-flight measurement per stage
+        // one in-flight measurement per stage: only THIS stage's previous pair is waited for (it finished a
+        // whole step ago), never the still-running tail of the previous step
+        prof_collect_one(stage);
         cudaEventRecord(g_prof.ev[stage][0], stream);
     }
     ~StageScope() {
