@@ -5,10 +5,11 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one view rendered forward+backward per GPU (config C3 of BASELINE.json: 1 M surfels,
-800x800, S = 8 material channels, SH degree 3, 6x512^2 logit cubemap with 6 mip levels). With N > 1
-every rank renders a different view of the same replicated cloud and one NCCL allreduce sums the
-per-surfel gradient arena + densification statistics (weak scaling; value = N views / step time).
+One "step" = one training step of a rank: VIEWS_PER_RANK (4) views of config C3 of BASELINE.json (1 M
+surfels, 800x800, S = 8 material channels, SH degree 3, 6x512^2 logit cubemap with 6 mip levels)
+rendered forward+backward with gradient accumulation. With N > 1 every rank renders different views of
+the same replicated cloud and ONE NCCL allreduce per step sums the per-surfel gradient arena +
+densification statistics (weak scaling: per-GPU work fixed; value = N * 4 views / step time).
 
 Prints ONE JSON line (see the driver contract in the task description). `--impl reference` runs the
 unmodified reference CUDA rasterizer from oracle/_ref through its own Python API on the same GPU
@@ -35,6 +36,7 @@ import torch  # noqa: E402
 
 WORKLOAD = dict(P=1_000_000, S=8, W=800, H=800, sh_degree=3, cube_res=512, min_res=16, opacity="trained")
 METRIC = "800x800 frames/s fwd+bwd at 1M surfels (rasterize + G-buffer + deferred PBR shading)"
+VIEWS_PER_RANK = 4   # views rendered per rank per step (gradient accumulation) before the single allreduce
 
 
 # ------------------------------------------------------------------------------------------------
@@ -194,30 +196,41 @@ class OursStep:
         return loss
 
     def step(self, i, e2e=False):
-        view = (i * self.world + self.rank) % len(self.cams)
+        """One training step of this rank: VIEWS_PER_RANK views rendered forward+backward with gradient
+        accumulation (autograd sums into .grad), then — when sharded — ONE allreduce of the flat
+        gradient arena + densification statistics (materialrefgs_b200/parallel.py)."""
         self.zero_grads()
-        if e2e:  # host -> device: camera + upstream-gradient maps (the per-step inputs); surfels are model state
-            cam_mats = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
-            up = {k: v.to(self.dev, non_blocking=True) for k, v in self.up_host.items()}
-        else:
-            c = self.cam_dev[view]
-            cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
-        loss = self.render(view, cam_mats, up)
+        V = VIEWS_PER_RANK
         if self.world > 1:
-            self.arena.zero_()
-            g = {k: v.grad for k, v in self.leaves.items()}
-            self.arena.accumulate_view(g, self.means2D.grad, self.last["radii"])
+            self.arena.stats.zero_()
+            self.arena.max_radii.zero_()
+        total = 0.0
+        for v in range(V):
+            view = ((i * V + v) * self.world + self.rank) % len(self.cams)
+            if e2e:  # host -> device: camera + upstream-gradient maps (per-view inputs); surfels are model state
+                cam_mats = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
+                up = {k: t.to(self.dev, non_blocking=True) for k, t in self.up_host.items()}
+            else:
+                c = self.cam_dev[view]
+                cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
+            self.means2D.grad = None   # the densification norm is taken per view (gaussian_model.py:1059-1061)
+            loss = self.render(view, cam_mats, up)
+            if self.world > 1:
+                self.arena.accumulate_view({}, self.means2D.grad, self.last["radii"])
+            if e2e:  # device -> host: the rendered image and the loss of every view
+                img = self.last["render"].detach().to("cpu", non_blocking=False)
+                total += float(loss.item()) + float(img[0, 0, 0])
+        if self.world > 1:
+            for name, view_t in self.arena.views.items():   # one flattening copy per step, then one allreduce
+                view_t.copy_(self.leaves[name].grad.reshape(view_t.shape))
             self.arena.allreduce()
-        if e2e:  # device -> host: the rendered image and the loss
-            img = self.last["render"].detach().to("cpu", non_blocking=False)
-            return float(loss.item()) + float(img[0, 0, 0])
-        return None
+        return total if e2e else None
 
     def h2d_bytes(self):
-        return sum(v.numel() * 4 for v in self.up_host.values()) + (16 + 16 + 3) * 4
+        return VIEWS_PER_RANK * (sum(v.numel() * 4 for v in self.up_host.values()) + (16 + 16 + 3) * 4)
 
     def d2h_bytes(self):
-        return 3 * WORKLOAD["H"] * WORKLOAD["W"] * 4 + 4
+        return VIEWS_PER_RANK * (3 * WORKLOAD["H"] * WORKLOAD["W"] * 4 + 4)
 
 
 class ReferenceStep(OursStep):
@@ -312,14 +325,17 @@ def cpu_shading_baseline():
 
 
 def main():
+    global VIEWS_PER_RANK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the surfel count (debug only)")
+    ap.add_argument("--views-per-rank", type=int, default=VIEWS_PER_RANK)
     a = ap.parse_args()
+    VIEWS_PER_RANK = max(1, a.views_per_rank)
     if a.P:
         WORKLOAD["P"] = a.P
     a.warmup = max(a.warmup, 3)
@@ -385,7 +401,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / a.steps
-    value = world_eff * 1000.0 / ms_per_step
+    value = world_eff * VIEWS_PER_RANK * 1000.0 / ms_per_step
 
     # ---- end-to-end timing: pinned host inputs -> device, result -> host, every step ----------
     for i in range(2):
@@ -413,10 +429,10 @@ def main():
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "C3: 1M random-init surfels (trained-like opacity), 800x800, S=8 material channels, "
                                "SH degree 3, rasterize + fused deferred PBR shading (6x512^2 cubemap, 6 mips), fwd+bwd",
-                   "P": P, "Pv": Pv, "N": N, "S": WORKLOAD["S"], "views_per_step": world_eff,
+                   "P": P, "Pv": Pv, "N": N, "S": WORKLOAD["S"], "views_per_step": world_eff * VIEWS_PER_RANK, "views_per_rank": VIEWS_PER_RANK,
                    "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the [P,66] gradient arena" if world_eff > 1 else ""),
                    "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient arenas) exceeds the 126 MB L2"},
-        "e2e": {"value": world_eff * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
+        "e2e": {"value": world_eff * VIEWS_PER_RANK * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
                 "d2h_bytes_per_step": stepper.d2h_bytes(),
                 "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss read back; surfel parameters are model state resident in HBM"},
         "clocks": clocks,
@@ -453,9 +469,10 @@ def main():
                         "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": stage_ms[dom],
                         "note": "tile-blend kernels are FP32-issue/MUFU bound (~160 flop/B), not HBM bound; see profiles/"}
     frame_bytes = ab["frame_raster"] + ab["frame_shade"]
+    ms_per_frame = ms_per_step / VIEWS_PER_RANK
     line["frame_roofline"] = {"algorithmic_bytes_per_frame": frame_bytes,
-                              "achieved_gbs": frame_bytes / (ms_per_step * 1e-3) / 1e9,
-                              "frac": frame_bytes / (ms_per_step * 1e-3) / 1e9 / peak}
+                              "achieved_gbs": frame_bytes / (ms_per_frame * 1e-3) / 1e9,
+                              "frac": frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak}
     line["stage_ms"] = stage_ms
     if not a.no_cpu_baseline and world_eff == 1:
         line["cpu_baseline"] = cpu_baseline()
