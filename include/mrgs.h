@@ -277,6 +277,21 @@ MRGS_API int mrgs_shade_backward(const MrgsShadeArgs* args, void* stream);
 MRGS_API int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs,
                                  const float* roughness, float* out, void* stream);
 
+/* ---- pseudo surface depth + depth_to_normal ------------------------------------------------------
+ * compute_2dgs_normal_and_regularizations (gaussian_renderer/__init__.py:50-78) + depth_to_normal
+ * (utils/point_utils.py:9-37) in one launch:
+ *   surf_depth  = (1-ratio) * nan_to_num(allmap[0]/allmap[1]) + ratio * nan_to_num(allmap[5])     [1,H,W]
+ *   surf_normal = normalize(cross(P[y+1]-P[y-1], P[x+1]-P[x-1])) * allmap[1] (detached), 0 on the border,
+ *                 with world points P(x,y) = surf_depth * (ray_matrix * (x,y,1)) + origin             [3,H,W]
+ * ray_matrix (row-major 3x3) = c2w rotation * inverse pinhole intrinsics with principal point (W/2,H/2).
+ * Backward: dL_dallmap planes 0 and 5 are written, plane 1 is ACCUMULATED (the shading backward owns it). */
+MRGS_API int mrgs_depth_normal_forward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
+                                       const float* host_origin, const float* allmap, float* surf_depth,
+                                       float* surf_normal, void* stream);
+MRGS_API int mrgs_depth_normal_backward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
+                                        const float* host_origin, const float* allmap, const float* dL_dsurf_depth,
+                                        const float* dL_dsurf_normal, float* dL_dallmap, void* stream);
+
 /* ---- EnvLight.build_mips on the device ----------------------------------------------------------
  * Cubemaps are float [6][res][res][C]. Replaces cubemap_mip (scene/light_utils.py:66-80) and the
  * renderutils_plugin ops diffuse_cubemap_fwd/bwd, specular_bounds, specular_cubemap_fwd/bwd

@@ -448,6 +448,44 @@ int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs
     return MRGS_OK;
 }
 
+int mrgs_depth_normal_forward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
+                              const float* host_origin, const float* allmap, float* surf_depth, float* surf_normal,
+                              void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!host_ray_matrix || !host_origin) {
+        set_error("mrgs_depth_normal_forward: null camera");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_FWD, stream, 1);
+        st = launch_depth_normal(false, width, height, depth_ratio, host_ray_matrix, host_origin, allmap, surf_depth,
+                                 surf_normal, nullptr, nullptr, nullptr, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("depth_normal_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_depth_normal_backward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
+                               const float* host_origin, const float* allmap, const float* dL_dsurf_depth,
+                               const float* dL_dsurf_normal, float* dL_dallmap, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!host_ray_matrix || !host_origin) {
+        set_error("mrgs_depth_normal_backward: null camera");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_BWD, stream, 1);
+        st = launch_depth_normal(true, width, height, depth_ratio, host_ray_matrix, host_origin, allmap, nullptr, nullptr,
+                                 dL_dsurf_depth, dL_dsurf_normal, dL_dallmap, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("depth_normal_bwd", stream, false);
+    return MRGS_OK;
+}
+
 #define MRGS_CUBE_CHECK(cond, who)                                  \
     if (!(cond)) {                                                  \
         set_error("%s: bad arguments", who);                        \

@@ -119,6 +119,10 @@ int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream);
 
+int launch_depth_normal(bool backward, int W, int H, float depth_ratio, const float* A, const float* o,
+                        const float* allmap, float* surf_depth, float* surf_normal, const float* g_depth,
+                        const float* g_normal, float* g_allmap, cudaStream_t stream);
+
 // ---- cubemap prefilter (EnvLight.build_mips) ---------------------------------------------------
 void launch_cubemap_mip_fwd(const float* in, float* out, int res_out, int C, cudaStream_t stream);
 void launch_cubemap_mip_bwd(const float* dout, float* din, int res_out, cudaStream_t stream);

@@ -360,3 +360,155 @@ int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs
 }
 
 }  // namespace mrgs
+
+// ---- pseudo surface depth + depth_to_normal --------------------------
+// compute_2dgs_normal_and_regularizations gaussian_renderer/__init__.py:50-78 and depth_to_normal /
+// depths_to_points utils/point_utils.py:9-37, fused: one thread per pixel evaluates the surface depth of
+// itself and of its 4 neighbours straight from the rasterizer's allmap (no intermediate maps), builds the
+// world points depth * (A (x,y,1)) + o and the normal of the centred differences.
+namespace mrgs {
+namespace {
+
+struct DepthNormalParams {
+    int W, H;
+    float depth_ratio;
+    float A[9];   // row-major: ray = A * (x, y, 1)
+    float o[3];   // camera centre
+    const float* allmap;
+    float* surf_depth;        // [1,H,W]
+    float* surf_normal;       // [3,H,W]
+    const float* g_depth;     // backward inputs (may be null)
+    const float* g_normal;
+    float* g_allmap;          // planes 0 and 5 written, plane 1 accumulated (+=)
+};
+
+__device__ __forceinline__ float nan_to_zero(float v) { return (isnan(v) || isinf(v)) ? 0.0f : v; }
+
+__device__ __forceinline__ float surf_depth_at(const DepthNormalParams& p, int x, int y) {
+    const size_t HW = (size_t)p.W * p.H, pix = (size_t)y * p.W + x;
+    const float expected = nan_to_zero(p.allmap[kDepthOff * HW + pix] / p.allmap[kAlphaOff * HW + pix]);
+    const float median = nan_to_zero(p.allmap[kMidDepthOff * HW + pix]);
+    return expected * (1.0f - p.depth_ratio) + p.depth_ratio * median;
+}
+
+__device__ __forceinline__ F3 ray_at(const DepthNormalParams& p, int x, int y) {
+    const float fx = (float)x, fy = (float)y;
+    return {p.A[0] * fx + p.A[1] * fy + p.A[2], p.A[3] * fx + p.A[4] * fy + p.A[5], p.A[6] * fx + p.A[7] * fy + p.A[8]};
+}
+
+__device__ __forceinline__ F3 cross3(F3 a, F3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+
+// normal at interior centre (x,y) from the four neighbour depths; optionally its vjp w.r.t. them
+struct CentreNormal {
+    F3 n;            // normalised
+    F3 rd, ru, rl, rr;  // rays of the down(y+1) / up(y-1) / left(x-1) / right(x+1) neighbours
+    F3 dx, dy, c;
+    float len;
+};
+__device__ __forceinline__ CentreNormal centre_normal(const DepthNormalParams& p, int x, int y, float d_dn,
+                                                      float d_up, float d_lf, float d_rt) {
+    CentreNormal r;
+    r.rd = ray_at(p, x, y + 1);
+    r.ru = ray_at(p, x, y - 1);
+    r.rl = ray_at(p, x - 1, y);
+    r.rr = ray_at(p, x + 1, y);
+    r.dx = d_dn * r.rd - d_up * r.ru;   // points[y+1] - points[y-1] (the origin cancels)
+    r.dy = d_rt * r.rr - d_lf * r.rl;   // points[x+1] - points[x-1]
+    r.c = cross3(r.dx, r.dy);
+    r.len = fmaxf(sqrtf(dot(r.c, r.c)), 1e-12f);  // F.normalize eps
+    r.n = (1.0f / r.len) * r.c;
+    return r;
+}
+
+__global__ void __launch_bounds__(256) depth_normal_fwd_kernel(const DepthNormalParams p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.W || y >= p.H) return;
+    const size_t HW = (size_t)p.W * p.H, pix = (size_t)y * p.W + x;
+    p.surf_depth[pix] = surf_depth_at(p, x, y);
+    F3 n = {0.f, 0.f, 0.f};
+    if (x >= 1 && y >= 1 && x < p.W - 1 && y < p.H - 1) {
+        const CentreNormal c = centre_normal(p, x, y, surf_depth_at(p, x, y + 1), surf_depth_at(p, x, y - 1),
+                                             surf_depth_at(p, x - 1, y), surf_depth_at(p, x + 1, y));
+        const float a = p.allmap[kAlphaOff * HW + pix];  // alpha.detach()
+        n = a * c.n;
+    }
+    p.surf_normal[pix] = n.x;
+    p.surf_normal[HW + pix] = n.y;
+    p.surf_normal[2 * HW + pix] = n.z;
+}
+
+// gradient of the loss w.r.t. the surface depth of pixel (x,y) through the normal of centre (cx,cy)
+__device__ __forceinline__ float depth_grad_via_centre(const DepthNormalParams& p, int cx, int cy, int x, int y) {
+    if (cx < 1 || cy < 1 || cx >= p.W - 1 || cy >= p.H - 1) return 0.0f;
+    const size_t HW = (size_t)p.W * p.H, cpix = (size_t)cy * p.W + cx;
+    const float a = p.allmap[kAlphaOff * HW + cpix];
+    const F3 g = {a * p.g_normal[cpix], a * p.g_normal[HW + cpix], a * p.g_normal[2 * HW + cpix]};
+    if (g.x == 0.f && g.y == 0.f && g.z == 0.f) return 0.0f;
+    const CentreNormal c = centre_normal(p, cx, cy, surf_depth_at(p, cx, cy + 1), surf_depth_at(p, cx, cy - 1),
+                                         surf_depth_at(p, cx - 1, cy), surf_depth_at(p, cx + 1, cy));
+    // n = c / max(|c|, eps)
+    F3 gc;
+    if (sqrtf(dot(c.c, c.c)) > 1e-12f)
+        gc = (1.0f / c.len) * (g - dot(c.n, g) * c.n);
+    else
+        gc = (1.0f / c.len) * g;
+    // c = dx x dy:  d/d(dx) = dy x gc,  d/d(dy) = gc x dx
+    const F3 g_dx = cross3(c.dy, gc), g_dy = cross3(gc, c.dx);
+    if (x == cx && y == cy + 1) return dot(g_dx, c.rd);
+    if (x == cx && y == cy - 1) return -dot(g_dx, c.ru);
+    if (x == cx + 1 && y == cy) return dot(g_dy, c.rr);
+    return -dot(g_dy, c.rl);
+}
+
+__global__ void __launch_bounds__(256) depth_normal_bwd_kernel(const DepthNormalParams p) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= p.W || y >= p.H) return;
+    const size_t HW = (size_t)p.W * p.H, pix = (size_t)y * p.W + x;
+    float g = p.g_depth ? p.g_depth[pix] : 0.0f;
+    if (p.g_normal) {
+        g += depth_grad_via_centre(p, x, y - 1, x, y);  // this pixel is the "down" neighbour of (x, y-1)
+        g += depth_grad_via_centre(p, x, y + 1, x, y);
+        g += depth_grad_via_centre(p, x - 1, y, x, y);
+        g += depth_grad_via_centre(p, x + 1, y, x, y);
+    }
+    // surf_depth = (1-ratio) * nan_to_num(D / alpha) + ratio * nan_to_num(median)
+    const float D = p.allmap[kDepthOff * HW + pix], a = p.allmap[kAlphaOff * HW + pix];
+    const float q = D / a;
+    const bool q_ok = !(isnan(q) || isinf(q));
+    const float ge = q_ok ? g * (1.0f - p.depth_ratio) : 0.0f;
+    const float med = p.allmap[kMidDepthOff * HW + pix];
+    // alpha == 0 (no contributor): the reference's autograd produces NaN here (0/0); nothing reads it, we write 0
+    p.g_allmap[kDepthOff * HW + pix] = q_ok ? ge / a : 0.0f;
+    p.g_allmap[kAlphaOff * HW + pix] += q_ok ? -ge * q / a : 0.0f;
+    p.g_allmap[kMidDepthOff * HW + pix] = (isnan(med) || isinf(med)) ? 0.0f : g * p.depth_ratio;
+}
+
+}  // namespace
+
+int launch_depth_normal(bool backward, int W, int H, float depth_ratio, const float* A, const float* o,
+                        const float* allmap, float* surf_depth, float* surf_normal, const float* g_depth,
+                        const float* g_normal, float* g_allmap, cudaStream_t stream) {
+    if (W <= 0 || H <= 0 || allmap == nullptr || (!backward && (!surf_depth || !surf_normal)) ||
+        (backward && !g_allmap)) {
+        set_error("mrgs_depth_normal: bad arguments");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    DepthNormalParams p;
+    p.W = W; p.H = H; p.depth_ratio = depth_ratio;
+    for (int i = 0; i < 9; ++i) p.A[i] = A[i];
+    for (int i = 0; i < 3; ++i) p.o[i] = o[i];
+    p.allmap = allmap; p.surf_depth = surf_depth; p.surf_normal = surf_normal;
+    p.g_depth = g_depth; p.g_normal = g_normal; p.g_allmap = g_allmap;
+    const dim3 grid((W + 31) / 32, (H + 7) / 8);
+    if (backward)
+        depth_normal_bwd_kernel<<<grid, 256, 0, stream>>>(p);
+    else
+        depth_normal_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    return MRGS_OK;
+}
+
+}  // namespace mrgs

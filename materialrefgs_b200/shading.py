@@ -33,6 +33,15 @@ def fg_lut(device) -> torch.Tensor:
     return _LUT_CACHE[key]
 
 
+def linear_to_srgb(linear, eps=None):
+    """utils/graphics_utils.py:102-110."""
+    if eps is None:
+        eps = torch.finfo(linear.dtype).eps
+    srgb0 = 323 / 25 * linear
+    srgb1 = (211 * linear.clamp_min(eps) ** (5 / 12) - 11) / 200
+    return torch.where(linear <= 0.0031308, srgb0, srgb1)
+
+
 def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
@@ -126,6 +135,60 @@ class _ShadeSurfel(torch.autograd.Function):
             d_levels.append(flat3[off:off + n].view(l.shape))
             off += n
         return (d_base, d_feat, d_allmap, None, None, *d_levels)
+
+
+def depth_ray_matrix(H, W, tanfovx, tanfovy, R) -> np.ndarray:
+    """A with world ray = A @ (x, y, 1) as depths_to_points builds it (utils/point_utils.py:9-24): the
+    pinhole recovered from full_proj_transform has its principal point at (W/2, H/2)."""
+    K = np.array([[W / (2.0 * tanfovx), 0.0, W / 2.0], [0.0, H / (2.0 * tanfovy), H / 2.0], [0.0, 0.0, 1.0]])
+    return (np.asarray(R, np.float64) @ np.linalg.inv(K)).astype(np.float32)
+
+
+class _SurfDepthNormal(torch.autograd.Function):
+    """allmap [7,H,W] -> (surf_depth [1,H,W], surf_normal [3,H,W]); compute_2dgs_normal_and_regularizations
+    (gaussian_renderer/__init__.py:50-78) + depth_to_normal (utils/point_utils.py:26-37) in one kernel."""
+
+    @staticmethod
+    def forward(ctx, allmap, cfg):
+        lib = _lib.load()
+        A, origin, ratio = cfg
+        allmap = allmap.contiguous()
+        dev = allmap.device
+        H, W = allmap.shape[1], allmap.shape[2]
+        depth = torch.empty((1, H, W), dtype=torch.float32, device=dev)
+        normal = torch.empty((3, H, W), dtype=torch.float32, device=dev)
+        Ac = (C.c_float * 9)(*[float(v) for v in np.asarray(A, np.float32).reshape(-1)])
+        oc = (C.c_float * 3)(*[float(v) for v in np.asarray(origin, np.float32).reshape(-1)])
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_depth_normal_forward(W, H, float(ratio), Ac, oc, allmap.data_ptr(), depth.data_ptr(),
+                                                     normal.data_ptr(), _stream(dev)), "mrgs_depth_normal_forward")
+        ctx.cfg = cfg
+        ctx.save_for_backward(allmap)
+        return depth, normal
+
+    @staticmethod
+    def backward(ctx, g_depth, g_normal):
+        lib = _lib.load()
+        (allmap,) = ctx.saved_tensors
+        A, origin, ratio = ctx.cfg
+        dev = allmap.device
+        H, W = allmap.shape[1], allmap.shape[2]
+        g_allmap = torch.zeros_like(allmap)
+        gd, gn = g_depth.contiguous(), g_normal.contiguous()
+        Ac = (C.c_float * 9)(*[float(v) for v in np.asarray(A, np.float32).reshape(-1)])
+        oc = (C.c_float * 3)(*[float(v) for v in np.asarray(origin, np.float32).reshape(-1)])
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_depth_normal_backward(W, H, float(ratio), Ac, oc, allmap.data_ptr(), gd.data_ptr(),
+                                                      gn.data_ptr(), g_allmap.data_ptr(), _stream(dev)),
+                       "mrgs_depth_normal_backward")
+        return g_allmap, None
+
+
+def surf_depth_normal(allmap, H, W, tanfovx, tanfovy, R, T, depth_ratio: float = 0.0):
+    """(surf_depth, surf_normal) of render_surfel's dict; R, T as stored on the reference's Camera."""
+    origin = -(np.asarray(R, np.float64) @ np.asarray(T, np.float64))
+    cfg = (depth_ray_matrix(H, W, tanfovx, tanfovy, R), origin.astype(np.float32), float(depth_ratio))
+    return _SurfDepthNormal.apply(allmap, cfg)
 
 
 def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, HWK, R, bg_color,

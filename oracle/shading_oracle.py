@@ -223,6 +223,44 @@ def shade_surfel(envmap, lut, rendered_image, rendered_features, allmap, cam, bg
             "refl_strength_map": refl_strength, "roughness_map": roughness, "base_color_map": albedo}
 
 
+def depths_to_points(cam, depthmap):
+    """utils/point_utils.py:9-24 (all in float32 torch ops like the reference)."""
+    dev = depthmap.device
+    w2v = torch.as_tensor(cam.world_view_transform, device=dev)
+    full = torch.as_tensor(cam.full_proj_transform, device=dev)
+    c2w = (w2v.T).inverse()
+    W, H = cam.image_width, cam.image_height
+    ndc2pix = torch.tensor([[W / 2, 0, 0, W / 2], [0, H / 2, 0, H / 2], [0, 0, 0, 1]], device=dev).float().T
+    projection_matrix = c2w.T @ full
+    intrins = (projection_matrix @ ndc2pix)[:3, :3].T
+    grid_x, grid_y = torch.meshgrid(torch.arange(W, device=dev).float(), torch.arange(H, device=dev).float(),
+                                    indexing="xy")
+    points = torch.stack([grid_x, grid_y, torch.ones_like(grid_x)], dim=-1).reshape(-1, 3)
+    rays_d = points @ intrins.inverse().T @ c2w[:3, :3].T
+    rays_o = c2w[:3, 3]
+    return depthmap.reshape(-1, 1) * rays_d + rays_o
+
+
+def depth_to_normal(cam, depth):
+    """utils/point_utils.py:26-37."""
+    points = depths_to_points(cam, depth).reshape(*depth.shape[1:], 3)
+    output = torch.zeros_like(points)
+    dx = points[2:, 1:-1] - points[:-2, 1:-1]
+    dy = points[1:-1, 2:] - points[1:-1, :-2]
+    output[1:-1, 1:-1, :] = F.normalize(torch.cross(dx, dy, dim=-1), dim=-1)
+    return output
+
+
+def surf_depth_normal(allmap, cam, depth_ratio=0.0):
+    """gaussian_renderer/__init__.py:50-78 (FLAG == "2dgs")."""
+    render_alpha = allmap[1:2]
+    median = torch.nan_to_num(allmap[5:6], 0, 0)
+    expected = torch.nan_to_num(allmap[0:1] / render_alpha, 0, 0)
+    surf_depth = expected * (1 - depth_ratio) + depth_ratio * median
+    surf_normal = depth_to_normal(cam, surf_depth).permute(2, 0, 1) * render_alpha.detach()
+    return surf_depth, surf_normal
+
+
 def synthetic_gbuffer(H, W, S=8, seed=5, device="cpu"):
     """Config C1 G-buffer: view-space normals scaled by alpha, alpha ~ U[0.5,1] with
     10 % zeros, albedo/roughness/refl/base ~ U[0,1]."""

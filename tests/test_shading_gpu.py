@@ -96,3 +96,38 @@ def test_get_specular_color_surfel_api():
                                            alpha, **args)
     assert (out - ref).abs().max().item() <= 1e-4
     assert (extra["direct_light"] - ref_extra["direct_light"]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("ratio,H,W", [(0.0, 96, 128), (0.35, 75, 101)])
+def test_surf_depth_and_depth_to_normal(ratio, H, W):
+    from materialrefgs_b200.shading import surf_depth_normal
+    cam = synthetic.orbit_camera(3, 8, W, H)
+    g = torch.Generator().manual_seed(17)
+    allmap = torch.zeros(7, H, W)
+    alpha = torch.rand(1, H, W, generator=g) * 0.6 + 0.4
+    alpha = alpha * (torch.rand(1, H, W, generator=g) > 0.1)          # holes: 0/0 -> nan_to_num
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, H), torch.linspace(0, 1, W), indexing="ij")
+    depth = 3.0 + 0.5 * torch.sin(6 * xx) * torch.cos(4 * yy) + 0.02 * torch.rand(H, W, generator=g)
+    allmap[0] = depth * alpha[0]
+    allmap[1:2] = alpha
+    allmap[5] = depth + 0.05
+    allmap = allmap.to(DEV)
+    wd = torch.randn(1, H, W, generator=g).to(DEV)
+    wn = torch.randn(3, H, W, generator=g).to(DEV)
+    a_o = allmap.clone().requires_grad_(True)
+    d_o, n_o = so.surf_depth_normal(a_o, cam.to(DEV), ratio)
+    ((d_o * wd).sum() + (n_o * wn).sum()).backward()
+    a_m = allmap.clone().requires_grad_(True)
+    d_m, n_m = surf_depth_normal(a_m, H, W, cam.tanfovx, cam.tanfovy, cam.R, cam.T, ratio)
+    ((d_m * wd).sum() + (n_m * wn).sum()).backward()
+    assert (d_m - d_o).abs().max().item() <= 1e-5
+    assert (n_m - n_o).abs().max().item() <= 2e-4          # normals of nearly flat 3x3 stencils amplify 1e-7 depth noise
+    assert not n_m[:, 0].any() and not n_m[:, :, -1].any()  # border stays zero
+    # where alpha == 0 the reference's autograd yields NaN (0/0 in the division backward); those pixels have no
+    # contributors, so the rasterizer backward never reads them — we return 0 there
+    ok = (allmap[1] > 0)
+    assert torch.isfinite(a_m.grad).all()
+    for pl in (0, 1, 5):
+        ref = a_o.grad[pl][ok]
+        assert ((a_m.grad[pl][ok] - ref).abs().max() / ref.abs().max().clamp_min(1e-20)).item() <= 2e-3, pl
+    assert not a_m.grad[[2, 3, 4, 6]].any()
