@@ -17,6 +17,8 @@
 // counts into global offsets -> stable scatter in which each warp owns a contiguous run of the block's
 // chunk, ranks its items with ballot-built peer masks + running per-(warp, digit) counters (no atomics
 // in the ranking), stages them in digit order in shared memory and writes coalesced runs.
+#include <stdlib.h>
+
 #include "kernels.cuh"
 
 namespace mrgs {
@@ -180,16 +182,82 @@ __global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restri
     }
 }
 
+// Digit histograms of ALL passes from one read of the keys: hist[pass][digit] (global totals).
+struct PassPlan {
+    int passes;
+    int shift[4];
+    int bits[4];
+};
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortThreads)
+radix_multi_hist_kernel(const KeyT* __restrict__ keys, int n, PassPlan plan, uint32_t* __restrict__ totals) {
+    __shared__ uint32_t s_hist[4][kMaxBins];
+    for (int i = threadIdx.x; i < 4 * kMaxBins; i += kSortThreads) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    const int base = blockIdx.x * kChunk;
+    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
+#pragma unroll 2
+    for (int k = 0; k < kItemsPerThread; ++k) {
+        const int i = base + k * kSortThreads + threadIdx.x;
+        const bool valid = i < n;
+        const uint32_t key = valid ? (uint32_t)keys[i] : 0u;
+        for (int ps = 0; ps < plan.passes; ++ps) {
+            const uint32_t d = (key >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1u);
+            const unsigned peers = warp_peers(d, plan.bits[ps], valid);
+            if (valid && (peers & lt) == 0) atomicAdd(&s_hist[ps][d], (uint32_t)__popc(peers));
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < plan.passes * kMaxBins; i += kSortThreads) {
+        const uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(&totals[i], c);
+    }
+}
+
+// totals[pass][256] -> starts[pass][256] (exclusive scan over digits), one CTA of 256 threads per pass
+__global__ void __launch_bounds__(256) radix_digit_scan_kernel(const uint32_t* __restrict__ totals, uint32_t* __restrict__ starts) {
+    __shared__ uint32_t s_warp[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t v = totals[blockIdx.x * kMaxBins + threadIdx.x];
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(kFullMask, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+        if (w < warp) before += s_warp[w];
+    starts[blockIdx.x * kMaxBins + threadIdx.x] = before + incl - v;
+}
+
+constexpr uint32_t kFlagPartial = 1u << 30, kFlagInclusive = 2u << 30, kValueMask = (1u << 30) - 1u;
+
 // Stable scatter of one radix pass. Item order inside a block: warp w owns items
 // [w*512, (w+1)*512) of the chunk, walked 32 at a time, so (warp, step, lane) is ascending item index.
 // Items are first placed at their block-local sorted position in shared memory, then written out so
 // that every digit's run leaves as contiguous, coalesced stores.
-template <typename KeyT, bool IOTA>
+// LOOKBACK = true makes the pass a single kernel (onesweep style): blocks take their chunk index from a
+// ticket, publish their digit counts in `status[block][digit]` (2 flag bits + 30 value bits in ONE word) and
+// obtain the exclusive prefix over earlier blocks by decoupled look-back; `block_off` then holds the
+// per-digit global starts. LOOKBACK = false expects block_off[digit][block] from a separate scan.
+template <typename KeyT, bool IOTA, bool LOOKBACK>
 __global__ void __launch_bounds__(kSortThreads, 3)
 radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
-                     const uint32_t* __restrict__ block_off, int num_blocks) {
+                     const uint32_t* __restrict__ block_off, int num_blocks, uint32_t* __restrict__ status,
+                     uint32_t* __restrict__ ticket) {
     const int bins = 1 << bits;
+    __shared__ int s_block;
+    if (LOOKBACK) {
+        if (threadIdx.x == 0) s_block = (int)atomicAdd(ticket, 1u);
+        __syncthreads();
+    }
+    const int block = LOOKBACK ? s_block : (int)blockIdx.x;
     __shared__ uint32_t s_cnt[kSortWarps][kMaxBins];  // per-warp digit counts -> local rank bases
     __shared__ uint32_t s_lstart[kMaxBins];           // block-local start of every digit
     __shared__ uint32_t s_gbase[kMaxBins];            // global start of this block's run of every digit
@@ -201,7 +269,7 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
     __syncthreads();
 
     const uint32_t mask = (uint32_t)bins - 1;
-    const int bbase = blockIdx.x * kChunk;
+    const int bbase = block * kChunk;
     const int wbase = bbase + warp * kWarpRun;
     KeyT key[kItemsPerThread];
     const unsigned lt = (1u << lane) - 1u;
@@ -242,7 +310,28 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
         if (d < bins) {
             uint32_t run = before + incl - tot;
             s_lstart[d] = run;
-            s_gbase[d] = block_off[(size_t)d * num_blocks + blockIdx.x];
+            if (LOOKBACK) {
+                uint32_t* mine = status + (size_t)block * kMaxBins + d;
+                volatile uint32_t* st = status;
+                if (block > 0) atomicExch(mine, kFlagPartial | tot);
+                uint32_t excl = 0;
+                int guard = 0;
+                for (int b = block - 1; b >= 0;) {
+                    const uint32_t sv = st[(size_t)b * kMaxBins + d];
+                    const uint32_t flag = sv & ~kValueMask;
+                    if (flag == 0) {
+                        if (++guard > (1 << 24)) break;  // never expected; avoids hanging the GPU on a logic error
+                        continue;
+                    }
+                    excl += sv & kValueMask;
+                    if (flag == kFlagInclusive) break;
+                    --b;
+                }
+                atomicExch(mine, kFlagInclusive | (excl + tot));
+                s_gbase[d] = block_off[d] + excl;
+            } else {
+                s_gbase[d] = block_off[(size_t)d * num_blocks + block];
+            }
 #pragma unroll
             for (int w = 0; w < kSortWarps; ++w) {
                 const uint32_t c = s_cnt[w][d];
@@ -281,40 +370,82 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
     }
 }
 
+static bool use_lookback() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("MRGS_RADIX_LOOKBACK");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+// scratch layout (uint32): totals[4][256] | starts[4][256] | tickets[64] | per-pass block tables
+constexpr size_t kScratchHeader = 4 * kMaxBins + 4 * kMaxBins + 64;
+
 template <typename KeyT>
 int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, int n, int total_bits,
-                     bool first_pass_iota, uint32_t* block_hist, cudaStream_t stream, KeyT** keys_final,
+                     bool first_pass_iota, uint32_t* scratch, cudaStream_t stream, KeyT** keys_final,
                      uint32_t** vals_final) {
-    // as few passes of <= 8 bits as possible, evenly split; block_hist = [256][blocks] counts followed
-    // by [passes][256] digit totals
+    // as few passes of <= 8 bits as possible, evenly split
     const int passes = (total_bits + 7) / 8;
     const int num_blocks = (n + kChunk - 1) / kChunk;
-    uint32_t* totals = block_hist + (size_t)kMaxBins * num_blocks;
-    cudaMemsetAsync(totals, 0, (size_t)passes * kMaxBins * sizeof(uint32_t), stream);
+    PassPlan plan{};
+    plan.passes = passes;
+    for (int pass = 0, shift = 0; pass < passes; ++pass) {
+        plan.bits[pass] = (total_bits - shift + (passes - pass) - 1) / (passes - pass);
+        plan.shift[pass] = shift;
+        shift += plan.bits[pass];
+    }
+    uint32_t* totals = scratch;
+    uint32_t* starts = scratch + 4 * kMaxBins;
+    uint32_t* tickets = scratch + 8 * kMaxBins;
+    uint32_t* tables = scratch + kScratchHeader;
+    const size_t table = (size_t)kMaxBins * num_blocks;
     KeyT* kin = keys_a;
     KeyT* kout = keys_b;
     uint32_t* vin = vals_a;
     uint32_t* vout = vals_b;
-    int shift = 0;
-    for (int pass = 0; pass < passes; ++pass) {
-        const int bits = (total_bits - shift + (passes - pass) - 1) / (passes - pass);
-        const int bins = 1 << bits;
-        uint32_t* tot = totals + (size_t)pass * kMaxBins;
-        radix_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, shift, bits, block_hist, tot, num_blocks);
-        radix_row_scan_kernel<<<bins, 256, 0, stream>>>(block_hist, tot, bins, num_blocks);
-        if (pass == 0 && first_pass_iota)
-            radix_scatter_kernel<KeyT, true><<<num_blocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, bits,
-                                                                                    block_hist, num_blocks);
-        else
-            radix_scatter_kernel<KeyT, false><<<num_blocks, kSortThreads, 0, stream>>>(kin, vin, kout, vout, n, shift, bits,
-                                                                                     block_hist, num_blocks);
-        KeyT* tk = kin; kin = kout; kout = tk;
-        uint32_t* tv = vin; vin = vout; vout = tv;
-        shift += bits;
+    int launches = 0;
+    if (use_lookback()) {
+        cudaMemsetAsync(scratch, 0, (kScratchHeader + (size_t)passes * table) * sizeof(uint32_t), stream);
+        radix_multi_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, plan, totals);
+        radix_digit_scan_kernel<<<passes, 256, 0, stream>>>(totals, starts);
+        launches += 2;
+        for (int pass = 0; pass < passes; ++pass) {
+            uint32_t* status = tables + (size_t)pass * table;
+            if (pass == 0 && first_pass_iota)
+                radix_scatter_kernel<KeyT, true, true><<<num_blocks, kSortThreads, 0, stream>>>(
+                    kin, vin, kout, vout, n, plan.shift[pass], plan.bits[pass], starts + pass * kMaxBins, num_blocks, status,
+                    tickets + pass);
+            else
+                radix_scatter_kernel<KeyT, false, true><<<num_blocks, kSortThreads, 0, stream>>>(
+                    kin, vin, kout, vout, n, plan.shift[pass], plan.bits[pass], starts + pass * kMaxBins, num_blocks, status,
+                    tickets + pass);
+            ++launches;
+            KeyT* tk = kin; kin = kout; kout = tk;
+            uint32_t* tv = vin; vin = vout; vout = tv;
+        }
+    } else {
+        cudaMemsetAsync(totals, 0, 4 * kMaxBins * sizeof(uint32_t), stream);
+        for (int pass = 0; pass < passes; ++pass) {
+            const int bits = plan.bits[pass], shift = plan.shift[pass];
+            uint32_t* tot = totals + (size_t)pass * kMaxBins;
+            radix_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, shift, bits, tables, tot, num_blocks);
+            radix_row_scan_kernel<<<1 << bits, 256, 0, stream>>>(tables, tot, 1 << bits, num_blocks);
+            if (pass == 0 && first_pass_iota)
+                radix_scatter_kernel<KeyT, true, false><<<num_blocks, kSortThreads, 0, stream>>>(
+                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr);
+            else
+                radix_scatter_kernel<KeyT, false, false><<<num_blocks, kSortThreads, 0, stream>>>(
+                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr);
+            launches += 3;
+            KeyT* tk = kin; kin = kout; kout = tk;
+            uint32_t* tv = vin; vin = vout; vout = tv;
+        }
     }
     *keys_final = kin;
     *vals_final = vin;
-    return passes * 3;
+    return launches;
 }
 
 // inclusive scan of tiles_touched gathered through the depth-sorted surfel order -------------------
@@ -446,7 +577,8 @@ identify_tile_ranges_kernel(int R, const uint16_t* __restrict__ keys, uint2* __r
 
 int sort_blocks(int64_t n) { return (int)((n + kChunk - 1) / kChunk); }
 size_t sort_hist_bytes(int64_t n) {
-    return ((size_t)kMaxBins * (size_t)(sort_blocks(n) > 0 ? sort_blocks(n) : 1) + 4 * kMaxBins) * sizeof(uint32_t);
+    const size_t blocks = (size_t)(sort_blocks(n) > 0 ? sort_blocks(n) : 1);
+    return (kScratchHeader + 4 * (size_t)kMaxBins * blocks) * sizeof(uint32_t);
 }
 int scan_blocks(int n) { return (n + kScanChunk - 1) / kScanChunk; }
 

@@ -72,21 +72,27 @@ render_bwd_kernel(const RenderBwdParams p) {
     const int warp_last = __reduce_max_sync(kFull, last_contributor);
     if (warp_last == 0) return;
 
-    float dL_dpix[NC];
+    float2 dL_dpix[NC / 2];  // channel pairs (2c, 2c+1)
 #pragma unroll
-    for (int c = 0; c < NC; ++c) dL_dpix[c] = 0.0f;
+    for (int c = 0; c < NC / 2; ++c) dL_dpix[c] = make_float2(0.0f, 0.0f);
     float dL_ddepth = 0.f, dL_daccum = 0.f, dL_dreg = 0.f, dL_dmedian = 0.f;
     float dL_dn0 = 0.f, dL_dn1 = 0.f, dL_dn2 = 0.f;
     float bg_dot_dpixel = 0.f;
     if (inside) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            dL_dpix[c] = p.dL_dcolor[c * HW + pix];
-            bg_dot_dpixel += p.background[c] * dL_dpix[c];
+        for (int c = 0; c < NC; ++c) {
+            float g = 0.0f;
+            if (c < 3) {
+                g = p.dL_dcolor[c * HW + pix];
+                bg_dot_dpixel += p.background[c] * g;
+            } else if (c - 3 < p.S) {
+                g = p.dL_dfeature[(c - 3) * HW + pix];
+            }
+            if (c & 1)
+                dL_dpix[c >> 1].y = g;
+            else
+                dL_dpix[c >> 1].x = g;
         }
-#pragma unroll
-        for (int c = 0; c < NC - 3; ++c)
-            if (c < p.S) dL_dpix[3 + c] = p.dL_dfeature[c * HW + pix];
         dL_ddepth = p.dL_dothers[kDepthOff * HW + pix];
         dL_daccum = p.dL_dothers[kAlphaOff * HW + pix];
         dL_dn0 = p.dL_dothers[(kNormalOff + 0) * HW + pix];
@@ -98,11 +104,11 @@ render_bwd_kernel(const RenderBwdParams p) {
 
     float T = T_final;
     float last_alpha = 0.f;
-    float accum_rec[NC], last_val[NC];
+    float2 accum_rec[NC / 2], last_val[NC / 2];
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        accum_rec[c] = 0.f;
-        last_val[c] = 0.f;
+    for (int c = 0; c < NC / 2; ++c) {
+        accum_rec[c] = make_float2(0.f, 0.f);
+        last_val[c] = make_float2(0.f, 0.f);
     }
     float last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
     float ln0 = 0.f, ln1 = 0.f, ln2 = 0.f, an0 = 0.f, an1 = 0.f, an2 = 0.f;
@@ -165,19 +171,30 @@ render_bwd_kernel(const RenderBwdParams p) {
                 T = T * inv_1ma;
                 const float w = alpha * T;
                 float dL_dalpha = 0.0f;
+                {
+                    // the per-channel recurrences run two channels per instruction (Blackwell packed fp32:
+                    // fma.rn.f32x2 / mul.rn.f32x2) — the kernel is issue bound, not FMA-pipe bound
+                    const float2 la2 = make_float2(last_alpha, last_alpha);
+                    const float2 oml2 = make_float2(1.0f - last_alpha, 1.0f - last_alpha);
+                    const float2 w2 = make_float2(w, w);
+                    const float2 neg1 = make_float2(-1.0f, -1.0f);
+                    float2 dsum = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int q = 0; q < NQ; ++q) {
-                    const float4 cv = s_cf[warp][q][j];
-                    const float cc[4] = {cv.x, cv.y, cv.z, cv.w};
+                    for (int q = 0; q < NQ; ++q) {
+                        const float4 cv = s_cf[warp][q][j];
+                        const float2 cc[2] = {make_float2(cv.x, cv.y), make_float2(cv.z, cv.w)};
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const int c = 4 * q + k;
-                        accum_rec[c] = last_alpha * last_val[c] + (1.0f - last_alpha) * accum_rec[c];
-                        last_val[c] = cc[k];
-                        dL_dalpha += (cc[k] - accum_rec[c]) * dL_dpix[c];
-                        const float gcf = w * dL_dpix[c];
-                        v[kGradColor + c] = gcf;
+                        for (int k = 0; k < 2; ++k) {
+                            const int c = 2 * q + k;
+                            accum_rec[c] = __ffma2_rn(la2, last_val[c], __fmul2_rn(oml2, accum_rec[c]));
+                            last_val[c] = cc[k];
+                            dsum = __ffma2_rn(__ffma2_rn(accum_rec[c], neg1, cc[k]), dL_dpix[c], dsum);
+                            const float2 gcf = __fmul2_rn(w2, dL_dpix[c]);
+                            v[kGradColor + 2 * c] = gcf.x;
+                            v[kGradColor + 2 * c + 1] = gcf.y;
+                        }
                     }
+                    dL_dalpha = dsum.x + dsum.y;
                 }
 
                 const float c_d = h.depth;

@@ -50,9 +50,9 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
     bool done = !inside;
     float T = 1.0f;
     uint32_t last_contributor = 0, median_contributor = 0;
-    float acc[NQ * 4];
+    float2 acc2[NQ * 2];  // channel pairs; packed fma.rn.f32x2 keeps each half an IEEE fma (bit-identical)
 #pragma unroll
-    for (int c = 0; c < NQ * 4; ++c) acc[c] = 0.0f;
+    for (int c = 0; c < NQ * 2; ++c) acc2[c] = make_float2(0.0f, 0.0f);
     float N0 = 0.f, N1 = 0.f, N2 = 0.f, D = 0.f, M1 = 0.f, M2 = 0.f, distortion = 0.f;
     float median_depth = 0.f;
 
@@ -120,13 +120,12 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
             N0 = __fmaf_rn(g3.x, w, N0);
             N1 = __fmaf_rn(g3.y, w, N1);
             N2 = __fmaf_rn(g3.z, w, N2);
+            const float2 w2 = make_float2(w, w);
 #pragma unroll
             for (int q = 0; q < NQ; ++q) {
                 const float4 v = s_cf[warp][q][j];
-                acc[4 * q + 0] = __fmaf_rn(w, v.x, acc[4 * q + 0]);
-                acc[4 * q + 1] = __fmaf_rn(w, v.y, acc[4 * q + 1]);
-                acc[4 * q + 2] = __fmaf_rn(w, v.z, acc[4 * q + 2]);
-                acc[4 * q + 3] = __fmaf_rn(w, v.w, acc[4 * q + 3]);
+                acc2[2 * q + 0] = __ffma2_rn(w2, make_float2(v.x, v.y), acc2[2 * q + 0]);
+                acc2[2 * q + 1] = __ffma2_rn(w2, make_float2(v.z, v.w), acc2[2 * q + 1]);
             }
             T = test_T;
             last_contributor = contributor;
@@ -142,6 +141,12 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
     reinterpret_cast<uint32_t*>(st)[3 * kTilePixels] = last_contributor;
     reinterpret_cast<uint32_t*>(st)[4 * kTilePixels] = median_contributor;
 
+    float acc[NQ * 4];
+#pragma unroll
+    for (int c = 0; c < NQ * 2; ++c) {
+        acc[2 * c] = acc2[c].x;
+        acc[2 * c + 1] = acc2[c].y;
+    }
     if (inside) {
         const size_t HW = (size_t)p.H * p.W;
         const size_t pix = (size_t)py * p.W + px;
