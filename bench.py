@@ -205,11 +205,15 @@ class OursStep:
             self.arena.stats.zero_()
             self.arena.max_radii.zero_()
         total = 0.0
+        view_of = lambda v: ((i * V + v) * self.world + self.rank) % len(self.cams)
+        if e2e:
+            self._e2e_prefetch(view_of(0))
         for v in range(V):
-            view = ((i * V + v) * self.world + self.rank) % len(self.cams)
+            view = view_of(v)
             if e2e:  # host -> device: camera + upstream-gradient maps (per-view inputs); surfels are model state
-                cam_mats = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
-                up = {k: t.to(self.dev, non_blocking=True) for k, t in self.up_host.items()}
+                cam_mats, up = self._e2e_take()
+                if v + 1 < V:
+                    self._e2e_prefetch(view_of(v + 1))   # next view's H2D overlaps this view's kernels
             else:
                 c = self.cam_dev[view]
                 cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
@@ -217,14 +221,61 @@ class OursStep:
             loss = self.render(view, cam_mats, up)
             if self.world > 1:
                 self.arena.accumulate_view({}, self.means2D.grad, self.last["radii"])
-            if e2e:  # device -> host: the rendered image and the loss of every view
-                img = self.last["render"].detach().to("cpu", non_blocking=False)
-                total += float(loss.item()) + float(img[0, 0, 0])
+            if e2e:  # device -> host: the rendered image and the loss of every view (copy stream, pinned target)
+                self._e2e_readback(v, loss)
+        if e2e:
+            self.copy_stream.synchronize()
+            total = float(sum(float(self.loss_host[v]) + float(self.img_host[v][0, 0, 0]) for v in range(V)))
         if self.world > 1:
             for name, view_t in self.arena.views.items():   # one flattening copy per step, then one allreduce
                 view_t.copy_(self.leaves[name].grad.reshape(view_t.shape))
             self.arena.allreduce()
         return total if e2e else None
+
+    # ---- end-to-end plumbing: pinned host buffers, one copy stream, double-buffered device inputs ----------
+    def _e2e_init(self):
+        if hasattr(self, "copy_stream"):
+            return
+        self.copy_stream = torch.cuda.Stream(device=self.dev)
+        self.in_slots = [None, None]
+        self.in_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free_events = [None, None]
+        self.slot = 0
+        self.img_host = [torch.empty((3, WORKLOAD["H"], WORKLOAD["W"]), dtype=torch.float32).pin_memory()
+                         for _ in range(VIEWS_PER_RANK)]
+        self.loss_host = torch.empty(VIEWS_PER_RANK, dtype=torch.float32).pin_memory()
+
+    def _e2e_prefetch(self, view):
+        self._e2e_init()
+        k = self.slot
+        main = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(self.copy_stream):
+            if self.free_events[k] is not None:
+                self.copy_stream.wait_event(self.free_events[k])   # the slot's previous consumer has finished
+            cam = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
+            up = {n: t.to(self.dev, non_blocking=True) for n, t in self.up_host.items()}
+            self.in_events[k].record(self.copy_stream)
+        self.in_slots[k] = (cam, up)
+        self.pending = k
+        self.slot ^= 1
+
+    def _e2e_take(self):
+        k = self.pending
+        torch.cuda.current_stream(self.dev).wait_event(self.in_events[k])
+        self.taken = k
+        return self.in_slots[k]
+
+    def _e2e_readback(self, v, loss):
+        main = torch.cuda.current_stream(self.dev)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.free_events[self.taken] = done
+        img = self.last["render"].detach()
+        with torch.cuda.stream(self.copy_stream):
+            self.copy_stream.wait_event(done)
+            self.img_host[v].copy_(img, non_blocking=True)
+            self.loss_host[v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        img.record_stream(self.copy_stream)
 
     def h2d_bytes(self):
         return VIEWS_PER_RANK * (sum(v.numel() * 4 for v in self.up_host.values()) + (16 + 16 + 3) * 4)
