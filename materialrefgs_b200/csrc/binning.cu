@@ -274,7 +274,12 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
     KeyT key[kItemsPerThread];
     const unsigned lt = (1u << lane) - 1u;
 
-    // phase 1: per-warp digit counts (keys stay in registers)
+    // phase 1: per-warp digit counts AND every item's rank inside its warp's run. The leader of each
+    // peer group bumps the warp's digit counter with one shared atomic; the value it gets back is the
+    // number of same-digit items in the warp's earlier steps (a warp's atomics to one address retire in
+    // program order), so rank = old + (peers before me in this step). Steps are independent apart from
+    // that atomic chain: all ballots overlap.
+    uint16_t rank[kItemsPerThread];
 #pragma unroll
     for (int k = 0; k < kItemsPerThread; ++k) {
         const int i = wbase + k * 32 + lane;
@@ -282,8 +287,11 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
         key[k] = valid ? keys_in[i] : (KeyT)0;
         const uint32_t d = ((uint32_t)key[k] >> shift) & mask;
         const unsigned peers = warp_peers(d, bits, valid);
-        if (valid && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
-        __syncwarp();
+        const int leader = __ffs(peers) - 1;
+        uint32_t old = 0;
+        if (valid && lane == leader) old = atomicAdd(&s_cnt[warp][d], (uint32_t)__popc(peers));
+        old = __shfl_sync(kFullMask, old, leader < 0 ? 0 : leader);
+        rank[k] = (uint16_t)(old + __popc(peers & lt));
     }
     __syncthreads();
     // phase 2: block-local exclusive scan over digits (bins <= 256 = one digit per thread), then the
@@ -341,19 +349,13 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
         }
     }
     __syncthreads();
-    // phase 3: rank, place at the block-local sorted position
+    // phase 3: place at the block-local sorted position (s_cnt now holds each warp's base per digit)
 #pragma unroll
     for (int k = 0; k < kItemsPerThread; ++k) {
         const int i = wbase + k * 32 + lane;
-        const bool valid = i < n;
-        const uint32_t d = ((uint32_t)key[k] >> shift) & mask;
-        const unsigned peers = warp_peers(d, bits, valid);
-        uint32_t pos = 0;
-        if (valid) pos = s_cnt[warp][d] + __popc(peers & lt);
-        __syncwarp();
-        if (valid && (peers & lt) == 0) s_cnt[warp][d] += __popc(peers);
-        __syncwarp();
-        if (valid) {
+        if (i < n) {
+            const uint32_t d = ((uint32_t)key[k] >> shift) & mask;
+            const uint32_t pos = s_cnt[warp][d] + rank[k];
             s_keys[pos] = key[k];
             s_vals[pos] = IOTA ? (uint32_t)i : vals_in[i];
         }
