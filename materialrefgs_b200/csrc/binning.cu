@@ -189,24 +189,54 @@ struct PassPlan {
     int bits[4];
 };
 
+// Every thread owns 16 CONSECUTIVE keys (one or two 16-byte loads per 8 keys) and run-length compresses
+// each pass's digit sequence in registers: consecutive instances belong to the same surfel (row-major
+// tiles), so the high tile bits repeat and one shared atomic covers a whole run; lanes are 16 items apart,
+// i.e. mostly different surfels, so simultaneous atomics rarely collide. No ballots.
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
 radix_multi_hist_kernel(const KeyT* __restrict__ keys, int n, PassPlan plan, uint32_t* __restrict__ totals) {
     __shared__ uint32_t s_hist[4][kMaxBins];
     for (int i = threadIdx.x; i < 4 * kMaxBins; i += kSortThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    const int base = blockIdx.x * kChunk;
-    const unsigned lt = (1u << (threadIdx.x & 31)) - 1u;
-#pragma unroll 2
-    for (int k = 0; k < kItemsPerThread; ++k) {
-        const int i = base + k * kSortThreads + threadIdx.x;
-        const bool valid = i < n;
-        const uint32_t key = valid ? (uint32_t)keys[i] : 0u;
-        for (int ps = 0; ps < plan.passes; ++ps) {
-            const uint32_t d = (key >> plan.shift[ps]) & ((1u << plan.bits[ps]) - 1u);
-            const unsigned peers = warp_peers(d, plan.bits[ps], valid);
-            if (valid && (peers & lt) == 0) atomicAdd(&s_hist[ps][d], (uint32_t)__popc(peers));
+    const int first = blockIdx.x * kChunk + threadIdx.x * kItemsPerThread;
+    uint32_t key[kItemsPerThread];
+    constexpr int kPerVec = 16 / (int)sizeof(KeyT);
+    if (first + kItemsPerThread <= n) {
+#pragma unroll
+        for (int v = 0; v < kItemsPerThread / kPerVec; ++v) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(keys + first + v * kPerVec);
+            const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+            for (int e = 0; e < kPerVec; ++e) {
+                if (sizeof(KeyT) == 4)
+                    key[v * kPerVec + e] = w[e];
+                else
+                    key[v * kPerVec + e] = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
+            }
         }
+    } else {
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) key[k] = (first + k < n) ? (uint32_t)keys[first + k] : 0u;
+    }
+    const int count = max(0, min(kItemsPerThread, n - first));
+    for (int ps = 0; ps < plan.passes; ++ps) {
+        const int shift = plan.shift[ps];
+        const uint32_t mask = (1u << plan.bits[ps]) - 1u;
+        uint32_t run_d = 0, run_n = 0;
+#pragma unroll
+        for (int k = 0; k < kItemsPerThread; ++k) {
+            if (k < count) {
+                const uint32_t d = (key[k] >> shift) & mask;
+                if (run_n != 0 && d != run_d) {
+                    atomicAdd(&s_hist[ps][run_d], run_n);
+                    run_n = 0;
+                }
+                run_d = d;
+                ++run_n;
+            }
+        }
+        if (run_n != 0) atomicAdd(&s_hist[ps][run_d], run_n);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < plan.passes * kMaxBins; i += kSortThreads) {
