@@ -394,13 +394,18 @@ def main():
     if not torch.cuda.is_available():
         print(json.dumps({"impl": a.impl, "unavailable": "no CUDA device"}))
         return 0
-    rank, local, world = dist_setup(a.gpus)
+    if a.impl == "reference":
+        # single-process arm: under torchrun rank 0 alone runs it, the other ranks leave without any work
+        # (no process group is created, so nobody waits on anybody)
+        if int(os.environ.get("RANK", "0")) != 0:
+            return 0
+        rank, local, world = 0, int(os.environ.get("LOCAL_RANK", "0")), 1
+        torch.cuda.set_device(local)
+    else:
+        rank, local, world = dist_setup(a.gpus)
     dev = torch.device("cuda", local)
 
     if a.impl == "reference":
-        if rank != 0 and world > 1:
-            barrier(world)
-            return 0
         world_eff = 1
         try:
             stepper = ReferenceStep(dev, 0, 1)
@@ -413,8 +418,6 @@ def main():
                     "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                                                 "d2h_bytes_per_step": 0}}
             print(json.dumps(line))
-            if world > 1:
-                barrier(world)
             return 0
     else:
         world_eff = world

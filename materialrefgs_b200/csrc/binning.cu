@@ -276,7 +276,7 @@ constexpr uint32_t kFlagPartial = 1u << 30, kFlagInclusive = 2u << 30, kValueMas
 // obtain the exclusive prefix over earlier blocks by decoupled look-back; `block_off` then holds the
 // per-digit global starts. LOOKBACK = false expects block_off[digit][block] from a separate scan.
 template <typename KeyT, bool IOTA, bool LOOKBACK>
-__global__ void __launch_bounds__(kSortThreads, 3)
+__global__ void __launch_bounds__(kSortThreads, 4)
 radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
                      const uint32_t* __restrict__ block_off, int num_blocks, uint32_t* __restrict__ status,

@@ -208,6 +208,10 @@ def mark_visible_raw(positions, viewmatrix, projmatrix):
     return present
 
 
+def _cpu_deep_copy_tuple(input_tuple):
+    return tuple(item.cpu().clone() if isinstance(item, torch.Tensor) else item for item in input_tuple)
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
                         cov3Ds_precomp, raster_settings):
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, features, opacities,
@@ -219,10 +223,20 @@ class _RasterizeGaussians(torch.autograd.Function):
     def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
                 cov3Ds_precomp, raster_settings):
         rs = raster_settings
-        (num_rendered, contrib, color, feature, depth, radii, geom, binning, image) = rasterize_forward_raw(
-            rs.bg, means3D, colors_precomp, features, opacities, scales, rotations, rs.scale_modifier,
-            cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
-            rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        args = (rs.bg, means3D, colors_precomp, features, opacities, scales, rotations, rs.scale_modifier,
+                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
+                rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
+        if rs.debug:  # same failure artefact as the reference (rast/diff_surfel_rasterization/__init__.py:87-94)
+            cpu_args = _cpu_deep_copy_tuple(args)
+            try:
+                outs = rasterize_forward_raw(*args)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_fw.dump")
+                print("\nAn error occured in forward. Please forward snapshot_fw.dump for debugging.")
+                raise ex
+        else:
+            outs = rasterize_forward_raw(*args)
+        (num_rendered, contrib, color, feature, depth, radii, geom, binning, image) = outs
         ctx.raster_settings = rs
         ctx.num_rendered = num_rendered
         ctx.save_for_backward(colors_precomp, features, means3D, scales, rotations, cov3Ds_precomp,

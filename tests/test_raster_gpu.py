@@ -196,6 +196,59 @@ def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
         assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
 
 
+@pytest.mark.parametrize("deg", [0, 1, 2])
+def test_lower_sh_degrees(ref_ext, deg):
+    """active_sh_degree < max degree: only (deg+1)^2 coefficients are read and receive gradients."""
+    import materialrefgs_b200.diff_surfel_rasterization as ours
+    dev = torch.device("cuda:0")
+    cloud, cam, grads = _scene(20_000, 8, 256, 192)
+    bg = torch.zeros(3, device=dev)
+    a = _run(ours, cloud, cam, bg, grads, sh_degree=deg)
+    b = _run(ref_ext, cloud, cam, bg, grads, sh_degree=deg)
+    assert (a["color"] - b["color"]).abs().max().item() <= IMG_ATOL
+    n = (deg + 1) ** 2
+    assert not a["grads"]["shs"][:, n:].any()
+    for k in a["grads"]:
+        assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
+
+
+def test_precomputed_transmat_path(ref_ext):
+    """cov3D_precomp (= the 3x3 ray-splat transform per surfel) instead of scales + rotations
+    (forward.cu:214-222, backward.cu:497-503, :570-584): outputs and dL/dtransMat against the reference."""
+    import materialrefgs_b200.diff_surfel_rasterization as ours
+    import materialrefgs_b200.rasterizer as raw
+    dev = torch.device("cuda:0")
+    P, S, W, H = 15_000, 8, 240, 160
+    cloud, cam, grads = _scene(P, S, W, H)
+    bg = torch.tensor([0.1, 0.0, 0.2], device=dev)
+    e = torch.empty(0, device=dev)
+    out = raw.rasterize_forward_raw(bg, cloud.means3D, e, cloud.features, cloud.opacities, cloud.scales, cloud.rotations,
+                                    1.0, e, cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy,
+                                    H, W, cloud.shs, 3, cam.camera_center, False, False)
+    T = refimpl.decode_mrgs_geom(out[6], P, S)["transMat"].clone()
+    T[out[5] <= 0] = 0.0     # culled rows are uninitialised scratch
+    res = {}
+    for name, mod in (("ours", ours), ("ref", ref_ext)):
+        Tl = T.clone().requires_grad_(True)
+        m3 = cloud.means3D.clone().requires_grad_(True)
+        op = cloud.opacities.clone().requires_grad_(True)
+        sh = cloud.shs.clone().requires_grad_(True)
+        m2 = torch.zeros_like(m3, requires_grad=True)
+        rast = mod.GaussianRasterizer(_settings(mod, cam, bg))
+        contrib, color, feat, radii, allmap = rast(means3D=m3, means2D=m2, opacities=op, shs=sh,
+                                                   features=cloud.features, cov3D_precomp=Tl)
+        gc, gf, go = grads
+        ((color * gc).sum() + (feat * gf).sum() + (allmap * go).sum()).backward()
+        res[name] = dict(color=color.detach(), allmap=allmap.detach(), radii=radii, gT=Tl.grad, gm3=m3.grad, gop=op.grad,
+                         gsh=sh.grad)
+    a, b = res["ours"], res["ref"]
+    assert torch.equal(a["radii"], b["radii"])
+    assert (a["color"] - b["color"]).abs().max().item() <= IMG_ATOL
+    assert (a["allmap"] - b["allmap"]).abs().max().item() <= IMG_ATOL
+    for k in ("gT", "gm3", "gop", "gsh"):
+        assert _rel_err(a[k], b[k]) <= 2 * GRAD_RTOL, k
+
+
 def test_scale_modifier_and_small_fov(ref_ext):
     """scale_modifier is honoured in the forward and ignored in the backward (reference quirk)."""
     import materialrefgs_b200.diff_surfel_rasterization as ours
