@@ -173,10 +173,16 @@ class OursStep:
         if world > 1:
             from materialrefgs_b200.parallel import GradArena
             self.arena = GradArena.create(WORKLOAD["P"], dev)
+            self.arena.bind(self.leaves)   # .grad of every parameter IS its arena segment
         self.last = {}
 
     def zero_grads(self):
-        for t in list(self.leaves.values()) + self.levels + [self.means2D]:
+        if self.world > 1:
+            self.arena.zero_()             # one memset: gradient segments + statistics tail
+            rest = self.levels + [self.means2D]
+        else:
+            rest = list(self.leaves.values()) + self.levels + [self.means2D]
+        for t in rest:
             t.grad = None
 
     def render(self, view, cam_mats, up):
@@ -197,13 +203,10 @@ class OursStep:
 
     def step(self, i, e2e=False):
         """One training step of this rank: VIEWS_PER_RANK views rendered forward+backward with gradient
-        accumulation (autograd sums into .grad), then — when sharded — ONE allreduce of the flat
+        accumulation (autograd sums into .grad = the arena segments), then — when sharded — ONE allreduce of the flat
         gradient arena + densification statistics (materialrefgs_b200/parallel.py)."""
         self.zero_grads()
         V = VIEWS_PER_RANK
-        if self.world > 1:
-            self.arena.stats.zero_()
-            self.arena.max_radii.zero_()
         total = 0.0
         view_of = lambda v: ((i * V + v) * self.world + self.rank) % len(self.cams)
         if e2e:
@@ -227,9 +230,7 @@ class OursStep:
             self.copy_stream.synchronize()
             total = float(sum(float(self.loss_host[v]) + float(self.img_host[v][0, 0, 0]) for v in range(V)))
         if self.world > 1:
-            for name, view_t in self.arena.views.items():   # one flattening copy per step, then one allreduce
-                view_t.copy_(self.leaves[name].grad.reshape(view_t.shape))
-            self.arena.allreduce()
+            self.arena.allreduce()         # autograd accumulated in place: no flattening copy
         return total if e2e else None
 
     # ---- end-to-end plumbing: pinned host buffers, one copy stream, double-buffered device inputs ----------
@@ -484,7 +485,7 @@ def main():
         "config": {"workload": "C3: 1M random-init surfels (trained-like opacity), 800x800, S=8 material channels, "
                                "SH degree 3, rasterize + fused deferred PBR shading (6x512^2 cubemap, 6 mips), fwd+bwd",
                    "P": P, "Pv": Pv, "N": N, "S": WORKLOAD["S"], "views_per_step": world_eff * VIEWS_PER_RANK, "views_per_rank": VIEWS_PER_RANK,
-                   "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the [P,66] gradient arena" if world_eff > 1 else ""),
+                   "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the P*68-float gradient+statistics arena" if world_eff > 1 else ""),
                    "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient arenas) exceeds the 126 MB L2"},
         "e2e": {"value": world_eff * VIEWS_PER_RANK * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
                 "d2h_bytes_per_step": stepper.d2h_bytes(),
@@ -541,4 +542,9 @@ def main():
 
 
 if __name__ == "__main__":
-    sys.exit(main())
+    rc = main()
+    sys.stdout.flush()
+    import torch.distributed as _dist
+    if _dist.is_available() and _dist.is_initialized():
+        _dist.destroy_process_group()
+    sys.exit(rc)

@@ -320,6 +320,16 @@ MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
 MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                       const float* projmatrix, uint8_t* present, void* stream);
 
+/* Densification statistics of one rendered view, one fused pass over the P surfels
+ * (GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061 and the max_radii2D update
+ * train_refnerf.py:1416-1418). For every surfel with radii > 0:
+ *   stats[i][0] += |dL_dmeans2D[i].xy|      (xyz_gradient_accum)
+ *   stats[i][1] += 1                        (denom)
+ *   max_radii[i] = max(max_radii[i], radii[i])
+ * dL_dmeans2D is [P,3] (the screen-space gradient the backward returns), stats [P,2], max_radii int32 [P]. */
+MRGS_API int mrgs_densify_stats(int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
+                                int32_t* max_radii, void* stream);
+
 #ifdef __cplusplus
 } /* extern "C" */
 #endif

@@ -126,6 +126,7 @@ SYMBOLS = {
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_densify_stats": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 
 _lib = None

@@ -205,6 +205,36 @@ int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
     return MRGS_OK;
 }
 
+namespace {
+__global__ void densify_stats_kernel(int P, const float* __restrict__ g, const int32_t* __restrict__ radii,
+                                     float2* __restrict__ stats, int32_t* __restrict__ max_radii) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P) return;
+    const int32_t r = radii[i];
+    if (r <= 0) return;
+    const float gx = g[3 * i], gy = g[3 * i + 1];
+    float2 s = stats[i];
+    s.x += sqrtf(gx * gx + gy * gy);
+    s.y += 1.0f;
+    stats[i] = s;
+    max_radii[i] = max(max_radii[i], r);
+}
+}  // namespace
+
+int mrgs_densify_stats(int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
+                       int32_t* max_radii, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (P < 0 || (P > 0 && (!dL_dmeans2D || !radii || !stats || !max_radii))) {
+        set_error("mrgs_densify_stats: bad arguments");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (P == 0) return MRGS_OK;
+    densify_stats_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, dL_dmeans2D, radii,
+                                                              reinterpret_cast<float2*>(stats), max_radii);
+    MRGS_LAUNCH_OK("densify_stats", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (a == nullptr) {

@@ -4,9 +4,10 @@ which is single-GPU and renders one view per iteration (train_refnerf.py:1168-11
   * evaluation: cameras are dealt round-robin to ranks, no collective (eval.py:23-74 renders
     independent cameras);
   * training step: a batch of views is split across ranks; every rank accumulates the per-surfel
-    parameter gradients of its views into ONE flat fp32 arena [P, F] and the densification
-    statistics into a second small arena; a single sum-allreduce over the gradient arena and one
-    max-allreduce over max_radii2D follow. Densification semantics follow
+    parameter gradients of its views into ONE flat fp32 arena (a contiguous segment per field,
+    bound as the parameters' .grad so autograd accumulates in place) with the densification
+    statistics at its tail; a single sum-allreduce over that arena and one max-allreduce over
+    max_radii2D follow. Densification semantics follow
     scene/gaussian_model.py:1059-1061 + train_refnerf.py:1416-1418: the norm of the screen-space
     gradient is taken PER VIEW, then summed; denom counts the views in which the surfel was visible.
 
@@ -31,8 +32,12 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
 
 @dataclass
 class GradArena:
-    """Flat [P, F] fp32 gradient buffer with named column views, plus densification statistics
-    (xyz_gradient_accum, denom packed as [P, 2]) and max_radii2D [P]."""
+    """ONE flat fp32 buffer holding, back to back, a contiguous [P, w] segment per gradient field and
+    the densification statistics (xyz_gradient_accum, denom packed as [P, 2]) at the tail, so that a
+    single sum-allreduce covers all of it; max_radii2D [P] (int32) needs a max-allreduce of its own.
+
+    Segments are contiguous so they can BE the parameters' .grad (bind()): autograd then accumulates
+    every view's gradient in place and no flattening copy precedes the allreduce."""
     flat: torch.Tensor
     views: Dict[str, torch.Tensor]
     stats: torch.Tensor
@@ -41,25 +46,55 @@ class GradArena:
     @staticmethod
     def create(P: int, device, fields: Sequence = GRAD_FIELDS) -> "GradArena":
         F = sum(w for _, w in fields)
-        flat = torch.zeros((P, F), dtype=torch.float32, device=device)
+        flat = torch.zeros((P * (F + 2),), dtype=torch.float32, device=device)
         views, o = {}, 0
         for name, w in fields:
-            views[name] = flat[:, o:o + w]
-            o += w
-        return GradArena(flat, views, torch.zeros((P, 2), dtype=torch.float32, device=device),
+            views[name] = flat[o:o + P * w].view(P, w)
+            o += P * w
+        return GradArena(flat, views, flat[o:o + 2 * P].view(P, 2),
                          torch.zeros((P,), dtype=torch.int32, device=device))
+
+    @property
+    def grads(self) -> torch.Tensor:
+        """The gradient part of the buffer (without the statistics tail), 1-D."""
+        return self.flat[:self.flat.numel() - self.stats.numel()]
 
     def zero_(self):
         self.flat.zero_()
-        self.stats.zero_()
         self.max_radii.zero_()
 
+    def bind(self, leaves: Dict[str, torch.Tensor]):
+        """Make each parameter's .grad a view of its arena segment (call once; zero_() per step).
+        With .grad present and grad mode off, autograd's accumulation is an in-place add, so the
+        storage stays the arena's."""
+        for name, v in self.views.items():
+            leaf = leaves.get(name)
+            if leaf is not None:
+                leaf.grad = v.view(leaf.shape)
+
+    def bound(self, leaves: Dict[str, torch.Tensor]) -> bool:
+        return all(leaves[n].grad is not None and leaves[n].grad.data_ptr() == v.data_ptr()
+                   for n, v in self.views.items() if n in leaves)
+
     def accumulate_view(self, grads: Dict[str, torch.Tensor], viewspace_grad: torch.Tensor, radii: torch.Tensor):
-        """Add one view's gradients; densification statistics use that view's own norm."""
+        """Add one view's gradients (those not already accumulated through bind()); the densification
+        statistics use that view's own norm. On the GPU the statistics are one libmrgs kernel
+        (mrgs_densify_stats); the torch expression below serves host tensors (the gloo tests)."""
         for name, v in self.views.items():
             g = grads.get(name)
             if g is not None:
                 v.add_(g.reshape(v.shape))
+        if viewspace_grad.is_cuda:
+            import ctypes as C
+            from . import _lib
+            lib = _lib.load()
+            P = radii.shape[0]
+            g = viewspace_grad.contiguous()
+            assert g.dtype == torch.float32 and g.shape == (P, 3) and radii.dtype == torch.int32
+            stream = torch.cuda.current_stream(g.device).cuda_stream
+            _lib.check(lib.mrgs_densify_stats(P, g.data_ptr(), radii.contiguous().data_ptr(), self.stats.data_ptr(),
+                                              self.max_radii.data_ptr(), C.c_void_p(stream)), "mrgs_densify_stats")
+            return
         vis = radii > 0
         norm = torch.linalg.norm(viewspace_grad[:, :2], dim=-1)
         self.stats[:, 0].add_(torch.where(vis, norm, torch.zeros_like(norm)))
@@ -67,11 +102,10 @@ class GradArena:
         torch.maximum(self.max_radii, torch.where(vis, radii, torch.zeros_like(radii)), out=self.max_radii)
 
     def allreduce(self, group=None):
-        """ONE sum-allreduce for gradients (+stats appended) and one max-allreduce for the radii."""
+        """ONE sum-allreduce for gradients + statistics and one max-allreduce for the radii."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(self.stats, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
 
 
@@ -79,7 +113,7 @@ def train_step_view_sharded(render_view: Callable[[int], Dict], n_views: int, ar
                             group=None) -> Dict[str, torch.Tensor]:
     """render_view(i) must run forward+backward of view i and return
     {'grads': {field: tensor}, 'viewspace_grad': [P,3], 'radii': [P]}. After the call every rank
-    holds the batch-summed gradients in arena.flat (== the sum of n_views reference iterations
+    holds the batch-summed gradients in arena.views (== the sum of n_views reference iterations
     without an optimizer step in between)."""
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1

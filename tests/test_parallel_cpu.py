@@ -37,6 +37,10 @@ def expected():
     return flat, stats, mx
 
 
+def _cat(arena):
+    return torch.cat([arena.views[n] for n, _ in parallel.GRAD_FIELDS], 1)
+
+
 def _worker(rank, world, port, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -50,7 +54,7 @@ def _worker(rank, world, port, q):
             return fake_view(i)
         views = parallel.train_step_view_sharded(render, NV, arena)
         ev = parallel.eval_views_sharded(lambda i: torch.tensor(float(i)), 7)
-        q.put((rank, seen, arena.flat.clone(), arena.stats.clone(), arena.max_radii.clone(),
+        q.put((rank, seen, _cat(arena), arena.stats.clone(), arena.max_radii.clone(),
                sorted(ev.keys()), views["shs"].shape))
     finally:
         dist.destroy_process_group()
@@ -88,6 +92,25 @@ def test_single_process_is_the_plain_sum():
     arena = parallel.GradArena.create(P, "cpu")
     parallel.train_step_view_sharded(fake_view, NV, arena)
     flat, stats, mx = expected()
-    assert torch.allclose(arena.flat, flat, atol=1e-5) and torch.allclose(arena.stats, stats, atol=1e-5)
+    assert torch.allclose(_cat(arena), flat, atol=1e-5) and torch.allclose(arena.stats, stats, atol=1e-5)
     assert torch.equal(arena.max_radii, mx)
     assert parallel.shard_views(10, 3, 4) == [3, 7]
+
+
+def test_bound_arena_receives_autograd_accumulation_in_place():
+    """bind(): the parameters' .grad ARE the arena segments, autograd adds every view into them and the
+    storage never moves (so no flattening copy is needed before the allreduce)."""
+    arena = parallel.GradArena.create(P, "cpu")
+    leaves = {n: torch.randn(P, 16, 3, requires_grad=True) if n == "shs" else torch.randn(P, w, requires_grad=True)
+              for n, w in parallel.GRAD_FIELDS}
+    arena.bind(leaves)
+    arena.zero_()
+    coef = [1.5, -2.0, 0.25]
+    for c in coef:
+        sum((l * l).sum() * c for l in leaves.values()).backward()
+    assert arena.bound(leaves)
+    for n, l in leaves.items():
+        assert torch.allclose(arena.views[n], (2 * sum(coef) * l.detach()).reshape(P, -1), atol=1e-5)
+    assert arena.grads.numel() == P * 66 and arena.flat.numel() == P * 68
+    arena.zero_()
+    assert float(leaves["shs"].grad.abs().max()) == 0.0
