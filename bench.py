@@ -208,7 +208,7 @@ class OursStep:
         self.zero_grads()
         V = VIEWS_PER_RANK
         total = 0.0
-        view_of = lambda v: ((i * V + v) * self.world + self.rank) % len(self.cams)
+        view_of = lambda v: ((i * V + v) * self.world + self.rank + i) % len(self.cams)   # + i: every rank cycles through all cameras
         if e2e:
             self._e2e_prefetch(view_of(0))
         for v in range(V):

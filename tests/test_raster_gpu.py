@@ -196,6 +196,77 @@ def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
         assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
 
 
+def test_c5_scale_view_batch_step_vs_reference(ref_ext):
+    """BASELINE config C5 on one rank: 5 M surfels, a view batch run through
+    parallel.train_step_view_sharded with the parameters' .grad bound to the gradient arena. The
+    batch-summed arena must equal the sum of the reference's per-view gradients, the densification
+    statistics the per-view norms (gaussian_model.py:1059-1061), and eval_views_sharded must return the
+    reference's images; binning of one view bit-exact."""
+    import materialrefgs_b200.diff_surfel_rasterization as ours
+    import materialrefgs_b200.rasterizer as raw
+    from materialrefgs_b200 import parallel
+    dev = torch.device("cuda:0")
+    P, S, W, H = 5_000_000, 8, 800, 800
+    cloud = synthetic.make_cloud(P, S=S, opacity="trained").to(dev)
+    cams = [synthetic.orbit_camera(v, 8, W, H).to(dev) for v in (0, 5)]
+    grads = tuple(t.to(dev) for t in synthetic.upstream_grads(S, H, W))
+    bg = torch.zeros(3, device=dev)
+    e = torch.empty(0, device=dev)
+    cam = cams[0]
+    args = (bg, cloud.means3D, e, cloud.features, cloud.opacities, cloud.scales, cloud.rotations, 1.0, e,
+            cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, cloud.shs, 3,
+            cam.camera_center, False, False)
+    R_ref, _, _, _, _, radii_r, _, bin_r, img_r = ref_ext._C.rasterize_gaussians(*args)
+    R, _, _, _, _, radii, geom, binning, img = raw.rasterize_forward_raw(*args)
+    assert R == R_ref and torch.equal(radii, radii_r)
+    bm = refimpl.decode_mrgs_binning(binning, R, refimpl.decode_mrgs_geom(geom, P, S)["depths"])
+    br = refimpl.decode_ref_binning(bin_r, R)
+    assert torch.equal(bm["keys"], br["keys"]) and torch.equal(bm["point_list"], br["point_list"])
+    im, ir = refimpl.decode_mrgs_image(img, H, W), refimpl.decode_ref_image(img_r, H, W)
+    assert torch.equal(im["ranges"], ir["ranges"][:im["ranges"].shape[0]])
+    assert torch.equal(im["n_contrib"], ir["n_contrib"][0])
+    del bin_r, img_r, geom, binning, img, bm, br, im, ir
+
+    names = ("means3D", "scales", "rotations", "opacities", "shs", "features")
+    leaves = {k: getattr(cloud, k).clone().requires_grad_(True) for k in names}
+    arena = parallel.GradArena.create(P, dev)
+    arena.bind(leaves)
+
+    def render_view(i):
+        c = cams[i]
+        rs = ours.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.world_view_transform,
+                                                c.full_proj_transform, 3, c.camera_center, False, False)
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        _, color, feat, rad, allmap = ours.GaussianRasterizer(rs)(
+            means3D=leaves["means3D"], means2D=m2, opacities=leaves["opacities"], shs=leaves["shs"],
+            features=leaves["features"], scales=leaves["scales"], rotations=leaves["rotations"])
+        ((color * grads[0]).sum() + (feat * grads[1]).sum() + (allmap * grads[2]).sum()).backward()
+        return {"grads": {}, "viewspace_grad": m2.grad, "radii": rad}
+
+    out = parallel.train_step_view_sharded(render_view, len(cams), arena)
+    assert arena.bound(leaves)
+    refs = [_run(ref_ext, cloud, c, bg, grads) for c in cams]
+    for k in names:
+        want = sum(r["grads"][k] for r in refs).reshape(P, -1)
+        assert _rel_err(out[k], want) <= 2 * GRAD_RTOL, k
+    norm = sum(torch.linalg.norm(r["grads"]["means2D"][:, :2], dim=-1) * (r["radii"] > 0) for r in refs)
+    assert _rel_err(arena.stats[:, 0], norm) <= 2 * GRAD_RTOL
+    assert torch.equal(arena.stats[:, 1], sum((r["radii"] > 0).float() for r in refs))
+    assert torch.equal(arena.max_radii, torch.maximum(refs[0]["radii"], refs[1]["radii"]).clamp_min(0))
+
+    def eval_view(i):
+        c = cams[i]
+        rs = ours.GaussianRasterizationSettings(H, W, c.tanfovx, c.tanfovy, bg, 1.0, c.world_view_transform,
+                                                c.full_proj_transform, 3, c.camera_center, False, False)
+        with torch.no_grad():
+            return ours.GaussianRasterizer(rs)(
+                means3D=cloud.means3D, means2D=None, opacities=cloud.opacities, shs=cloud.shs,
+                features=cloud.features, scales=cloud.scales, rotations=cloud.rotations)[1]
+    imgs = parallel.eval_views_sharded(eval_view, len(cams))
+    for i, r in enumerate(refs):
+        assert (imgs[i] - r["color"]).abs().max().item() <= IMG_ATOL
+
+
 @pytest.mark.parametrize("deg", [0, 1, 2])
 def test_lower_sh_degrees(ref_ext, deg):
     """active_sh_degree < max degree: only (deg+1)^2 coefficients are read and receive gradients."""
