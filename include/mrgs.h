@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 3
+#define MRGS_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -151,9 +151,17 @@ typedef struct MrgsForwardArgs {
     void* geom_buffer;   size_t geom_bytes;
     void* image_buffer;  size_t image_bytes;
     mrgs_alloc_fn binning_alloc;   void* binning_ctx;
+    /* Optional, optimistic binning. binning_scratch is a device buffer of at least
+     * mrgs_binning_bytes(binning_capacity) bytes the caller guesses to be large enough (e.g. 1.25 x the
+     * previous frame's R). With it the call enqueues instance expansion, tile sort, ranges and the blend
+     * BEFORE it waits for R (the kernels read the count from device memory), so the host wait overlaps
+     * queued GPU work instead of draining the stream. If R > binning_capacity the call falls back to
+     * binning_alloc and redoes those stages; results are identical either way. 0 / NULL = exact path only. */
+    void* binning_scratch;  size_t binning_scratch_bytes;  int64_t binning_capacity;
     /* results */
     int32_t num_rendered;          /* R, also the reference's first return value        */
-    void* binning_buffer;          /* what binning_alloc returned (NULL if R == 0)      */
+    void* binning_buffer;          /* binning_scratch, or what binning_alloc returned (NULL if R == 0) */
+    int64_t binning_capacity_used; /* instance count binning_buffer is laid out for (mrgs_binning_layout) */
 } MrgsForwardArgs;
 
 typedef struct MrgsBackwardArgs {

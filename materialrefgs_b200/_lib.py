@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 3
+MRGS_ABI_VERSION = 4
 MAX_FEATURES = 24
 TILE = 16
 
@@ -52,7 +52,8 @@ class ForwardArgs(C.Structure):
         ("geom_buffer", _fp), ("geom_bytes", C.c_size_t),
         ("image_buffer", _fp), ("image_bytes", C.c_size_t),
         ("binning_alloc", alloc_fn), ("binning_ctx", C.c_void_p),
-        ("num_rendered", C.c_int32), ("binning_buffer", _fp),
+        ("binning_scratch", _fp), ("binning_scratch_bytes", C.c_size_t), ("binning_capacity", C.c_int64),
+        ("num_rendered", C.c_int32), ("binning_buffer", _fp), ("binning_capacity_used", C.c_int64),
     ]
 
 

@@ -37,6 +37,14 @@ static int32_t* pinned_slot() {
     return slot;
 }
 
+static cudaEvent_t r_ready_event() {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (ev == nullptr) {
+        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    }
+    return ev;
+}
+
 // ---- optional per-stage timing (CUDA events on the launching stream) + own-kernel launch count
 struct Profiler {
     bool enabled = false;
@@ -243,6 +251,7 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
     }
     a->num_rendered = 0;
     a->binning_buffer = nullptr;
+    a->binning_capacity_used = 0;
     if (a->P < 0 || a->width <= 0 || a->height <= 0) {
         set_error("mrgs_forward: bad sizes P=%d W=%d H=%d", a->P, a->width, a->height);
         return MRGS_ERR_INVALID_ARGUMENT;
@@ -356,46 +365,37 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         }
         MRGS_LAUNCH_OK("scan", stream, debug);
 
-        // R has to reach the host to size the binning buffer (same point as
-        // rasterizer_impl.cu:287, but through pinned memory on the caller's stream)
+        rp.rec = pp.rec;
+        rp.cf = pp.cf;
+        rp.bbox = pp.bbox;
+
+        // R has to reach the host: it sizes the binning buffer and is the call's first result (same point
+        // as rasterizer_impl.cu:287, but through pinned memory on the caller's stream).
         int32_t* slot = pinned_slot();
-        if (slot == nullptr) {
-            set_error("mrgs_forward: cudaHostAlloc failed");
+        cudaEvent_t r_ready = r_ready_event();
+        if (slot == nullptr || r_ready == nullptr) {
+            set_error("mrgs_forward: cudaHostAlloc / cudaEventCreate failed");
             return MRGS_ERR_CUDA;
         }
-        MRGS_CUDA_OK(cudaMemcpyAsync(slot, offsets + a->P - 1, sizeof(int32_t),
-                                     cudaMemcpyDeviceToHost, stream));
-        MRGS_CUDA_OK(cudaStreamSynchronize(stream));
-        R = *slot;
-        if (R < 0) {
-            set_error("mrgs_forward: instance count overflow (R=%d)", R);
-            return MRGS_ERR_UNSUPPORTED;
-        }
+        const uint32_t* R_dev = offsets + a->P - 1;
+        MRGS_CUDA_OK(cudaMemcpyAsync(slot, R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+        MRGS_CUDA_OK(cudaEventRecord(r_ready, stream));
 
-        if (R > 0) {
+        // instance expansion, tile sort, tile ranges and the blend for a binning buffer laid out for
+        // `cap` instances; with dev_count the kernels take the real count from the device
+        auto bin_and_render = [&](char* bin, int64_t cap, const uint32_t* dev_count) -> int {
             MrgsBinningLayout bl;
-            if (mrgs_binning_layout(R, &bl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
-            if (a->binning_alloc == nullptr) {
-                set_error("mrgs_forward: binning_alloc callback is null");
-                return MRGS_ERR_INVALID_ARGUMENT;
-            }
-            char* bin = (char*)a->binning_alloc(a->binning_ctx, bl.total);
-            if (bin == nullptr) {
-                set_error("mrgs_forward: binning_alloc(%zu) returned null", bl.total);
-                return MRGS_ERR_WORKSPACE;
-            }
-            a->binning_buffer = bin;
+            if (mrgs_binning_layout(cap, &bl) != MRGS_OK) return MRGS_ERR_INVALID_ARGUMENT;
             uint16_t* keys_a = (uint16_t*)(bin + bl.keys);
             uint16_t* keys_b = (uint16_t*)(bin + bl.keys_unsorted);
             uint32_t* vals_a = (uint32_t*)(bin + bl.point_list);
             uint32_t* vals_b = (uint32_t*)(bin + bl.point_list_unsorted);
-
             {
                 StageScope sc(MRGS_STAGE_DUPLICATE, stream, 1);
-                launch_emit_instances(a->P, order, pp.tiles_touched, pp.rect, offsets, keys_a, vals_a, grid_x, stream);
+                launch_emit_instances(a->P, order, pp.tiles_touched, pp.rect, offsets, keys_a, vals_a, grid_x,
+                                      (uint32_t)cap, stream);
             }
             MRGS_LAUNCH_OK("emit_instances", stream, debug);
-
             // two stable passes over the tile bits only; an even pass count leaves the result in A
             const int tile_bits = (int)higher_msb((uint32_t)tiles);
             uint16_t* keys_sorted = nullptr;
@@ -403,8 +403,8 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
             {
                 int launches = 0;
                 StageScope sc(MRGS_STAGE_SORT, stream, 0);
-                tile_sort(keys_a, keys_b, vals_a, vals_b, R, tile_bits < 9 ? 9 : tile_bits, (uint32_t*)(bin + bl.sort_temp),
-                          stream, &keys_sorted, &vals_sorted, &launches);
+                tile_sort(keys_a, keys_b, vals_a, vals_b, (int)cap, tile_bits < 9 ? 9 : tile_bits,
+                          (uint32_t*)(bin + bl.sort_temp), stream, &keys_sorted, &vals_sorted, &launches, dev_count);
                 g_prof.launches += launches;
             }
             MRGS_LAUNCH_OK("tile_sort", stream, debug);
@@ -412,21 +412,66 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
                 set_error("mrgs_forward: internal error, tile sort result not in buffer A");
                 return MRGS_ERR_CUDA;
             }
-
             {
                 StageScope sc(MRGS_STAGE_RANGES, stream, 1);
-                launch_identify_tile_ranges(R, keys_sorted, ranges, stream);
+                launch_identify_tile_ranges((int)cap, dev_count, keys_sorted, ranges, stream);
             }
             MRGS_LAUNCH_OK("identify_tile_ranges", stream, debug);
-
             rp.point_list = vals_sorted;
+            int st;
+            {
+                StageScope sc(MRGS_STAGE_RENDER_FWD, stream, 1);
+                st = launch_render_fwd(rp, stream);
+            }
+            if (st != MRGS_OK) return st;
+            MRGS_LAUNCH_OK("render_fwd", stream, debug);
+            return MRGS_OK;
+        };
+
+        // Optimistic path: the caller lent a buffer sized for binning_capacity instances, so everything up
+        // to the blend is enqueued BEFORE the host waits for R; the wait then overlaps queued GPU work
+        // instead of draining the stream. If R turns out larger, the exact path below redoes the binning.
+        bool rendered = false;
+        const int64_t cap = a->binning_capacity;
+        if (cap > 0 && cap <= 0x7fffffff && a->binning_scratch != nullptr && radix_lookback_enabled() &&
+            a->binning_scratch_bytes >= mrgs_binning_bytes(cap)) {
+            const int st = bin_and_render((char*)a->binning_scratch, cap, R_dev);
+            if (st != MRGS_OK) return st;
+            rendered = true;
         }
-        rp.rec = pp.rec;
-        rp.cf = pp.cf;
-        rp.bbox = pp.bbox;
+        MRGS_CUDA_OK(cudaEventSynchronize(r_ready));
+        R = *slot;
+        if (R < 0) {
+            set_error("mrgs_forward: instance count overflow (R=%d)", R);
+            return MRGS_ERR_UNSUPPORTED;
+        }
+        if (rendered && R <= cap) {
+            a->binning_buffer = a->binning_scratch;
+            a->binning_capacity_used = cap;
+        } else if (R > 0) {
+            if (a->binning_alloc == nullptr) {
+                set_error("mrgs_forward: binning_alloc callback is null");
+                return MRGS_ERR_INVALID_ARGUMENT;
+            }
+            const size_t need = mrgs_binning_bytes(R);
+            char* bin = (char*)a->binning_alloc(a->binning_ctx, need);
+            if (bin == nullptr) {
+                set_error("mrgs_forward: binning_alloc(%zu) returned null", need);
+                return MRGS_ERR_WORKSPACE;
+            }
+            if (rendered) MRGS_CUDA_OK(cudaMemsetAsync(ranges, 0, (size_t)tiles * sizeof(uint2), stream));
+            const int st = bin_and_render(bin, R, nullptr);
+            if (st != MRGS_OK) return st;
+            a->binning_buffer = bin;
+            a->binning_capacity_used = R;
+            rendered = true;
+        }
+        a->num_rendered = R;
+        if (rendered) return MRGS_OK;
     }
     a->num_rendered = R;
 
+    // no surfels or no instances: the blend still writes background / zero maps
     int st;
     {
         StageScope sc(MRGS_STAGE_RENDER_FWD, stream, 1);

@@ -195,7 +195,10 @@ struct PassPlan {
 // i.e. mostly different surfels, so simultaneous atomics rarely collide. No ballots.
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortThreads)
-radix_multi_hist_kernel(const KeyT* __restrict__ keys, int n, PassPlan plan, uint32_t* __restrict__ totals) {
+radix_multi_hist_kernel(const KeyT* __restrict__ keys, int n, const uint32_t* __restrict__ n_dev, PassPlan plan,
+                        uint32_t* __restrict__ totals) {
+    if (n_dev != nullptr) n = min(n, (int)*n_dev);   // launched for a capacity, the count lives on the device
+    if ((long long)blockIdx.x * kChunk >= n) return;
     __shared__ uint32_t s_hist[4][kMaxBins];
     for (int i = threadIdx.x; i < 4 * kMaxBins; i += kSortThreads) (&s_hist[0][0])[i] = 0;
     __syncthreads();
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(kSortThreads, 4)
 radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
                      KeyT* __restrict__ keys_out, uint32_t* __restrict__ vals_out, int n, int shift, int bits,
                      const uint32_t* __restrict__ block_off, int num_blocks, uint32_t* __restrict__ status,
-                     uint32_t* __restrict__ ticket) {
+                     uint32_t* __restrict__ ticket, const uint32_t* __restrict__ n_dev) {
     const int bins = 1 << bits;
     __shared__ int s_block;
     if (LOOKBACK) {
@@ -288,6 +291,8 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
         __syncthreads();
     }
     const int block = LOOKBACK ? s_block : (int)blockIdx.x;
+    if (n_dev != nullptr) n = min(n, (int)*n_dev);   // grid sized for a capacity: surplus blocks leave at once
+    if ((long long)block * kChunk >= n) return;
     __shared__ uint32_t s_cnt[kSortWarps][kMaxBins];  // per-warp digit counts -> local rank bases
     __shared__ uint32_t s_lstart[kMaxBins];           // block-local start of every digit
     __shared__ uint32_t s_gbase[kMaxBins];            // global start of this block's run of every digit
@@ -417,7 +422,7 @@ constexpr size_t kScratchHeader = 4 * kMaxBins + 4 * kMaxBins + 64;
 template <typename KeyT>
 int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* vals_b, int n, int total_bits,
                      bool first_pass_iota, uint32_t* scratch, cudaStream_t stream, KeyT** keys_final,
-                     uint32_t** vals_final) {
+                     uint32_t** vals_final, const uint32_t* n_dev = nullptr) {
     // as few passes of <= 8 bits as possible, evenly split
     const int passes = (total_bits + 7) / 8;
     const int num_blocks = (n + kChunk - 1) / kChunk;
@@ -440,7 +445,7 @@ int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* val
     int launches = 0;
     if (use_lookback()) {
         cudaMemsetAsync(scratch, 0, (kScratchHeader + (size_t)passes * table) * sizeof(uint32_t), stream);
-        radix_multi_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, plan, totals);
+        radix_multi_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, n_dev, plan, totals);
         radix_digit_scan_kernel<<<passes, 256, 0, stream>>>(totals, starts);
         launches += 2;
         for (int pass = 0; pass < passes; ++pass) {
@@ -448,11 +453,11 @@ int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* val
             if (pass == 0 && first_pass_iota)
                 radix_scatter_kernel<KeyT, true, true><<<num_blocks, kSortThreads, 0, stream>>>(
                     kin, vin, kout, vout, n, plan.shift[pass], plan.bits[pass], starts + pass * kMaxBins, num_blocks, status,
-                    tickets + pass);
+                    tickets + pass, n_dev);
             else
                 radix_scatter_kernel<KeyT, false, true><<<num_blocks, kSortThreads, 0, stream>>>(
                     kin, vin, kout, vout, n, plan.shift[pass], plan.bits[pass], starts + pass * kMaxBins, num_blocks, status,
-                    tickets + pass);
+                    tickets + pass, n_dev);
             ++launches;
             KeyT* tk = kin; kin = kout; kout = tk;
             uint32_t* tv = vin; vin = vout; vout = tv;
@@ -466,10 +471,10 @@ int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* val
             radix_row_scan_kernel<<<1 << bits, 256, 0, stream>>>(tables, tot, 1 << bits, num_blocks);
             if (pass == 0 && first_pass_iota)
                 radix_scatter_kernel<KeyT, true, false><<<num_blocks, kSortThreads, 0, stream>>>(
-                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr);
+                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr, nullptr);
             else
                 radix_scatter_kernel<KeyT, false, false><<<num_blocks, kSortThreads, 0, stream>>>(
-                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr);
+                    kin, vin, kout, vout, n, shift, bits, tables, num_blocks, nullptr, nullptr, nullptr);
             launches += 3;
             KeyT* tk = kin; kin = kout; kout = tk;
             uint32_t* tv = vin; vin = vout; vout = tv;
@@ -547,7 +552,7 @@ gather_scan_kernel(const uint32_t* __restrict__ order, const uint32_t* __restric
 __global__ void __launch_bounds__(256)
 emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
                       const uint2* __restrict__ rect, const uint32_t* __restrict__ offsets_incl,
-                      uint16_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x) {
+                      uint16_t* __restrict__ keys, uint32_t* __restrict__ values, int grid_x, uint32_t capacity) {
     __shared__ uint32_t s_end[8][32];
     __shared__ uint32_t s_id[8][32];
     __shared__ uint2 s_rect[8][32];
@@ -571,7 +576,8 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
     s_id[warp][lane] = id;
     if (k < P && end > begin_mine) s_rect[warp][lane] = rect[id];
     __syncwarp();
-    for (uint32_t pos = seg_begin + lane; pos < seg_end; pos += 32) {
+    const uint32_t stop = min(seg_end, capacity);   // never write past the buffer the caller sized
+    for (uint32_t pos = seg_begin + lane; pos < stop; pos += 32) {
         // first lane j with s_end[j] > pos
         int lo = 0;
 #pragma unroll
@@ -589,7 +595,9 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
 }
 
 __global__ void __launch_bounds__(256)
-identify_tile_ranges_kernel(int R, const uint16_t* __restrict__ keys, uint2* __restrict__ ranges) {
+identify_tile_ranges_kernel(int R, const uint32_t* __restrict__ n_dev, const uint16_t* __restrict__ keys,
+                            uint2* __restrict__ ranges) {
+    if (n_dev != nullptr) R = min(R, (int)*n_dev);
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= R) return;
     const uint32_t tile = keys[idx];
@@ -632,20 +640,23 @@ int offsets_in_order(const uint32_t* order, const uint32_t* tiles_touched, int P
 
 void launch_emit_instances(int P, const uint32_t* order, const uint32_t* tiles_touched, const uint2* rect,
                            const uint32_t* offsets_incl, uint16_t* keys, uint32_t* values, int grid_x,
-                           cudaStream_t stream) {
+                           uint32_t capacity, cudaStream_t stream) {
     emit_instances_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, order, tiles_touched, rect, offsets_incl, keys, values,
-                                                              grid_x);
+                                                              grid_x, capacity);
 }
 
 int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int R, int tile_bits,
-              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches) {
+              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches,
+              const uint32_t* R_dev) {
     *launches = radix_sort_pairs<uint16_t>(keys_a, keys_b, vals_a, vals_b, R, tile_bits, false, block_hist, stream,
-                                           keys_sorted, vals_sorted);
+                                           keys_sorted, vals_sorted, R_dev);
     return MRGS_OK;
 }
 
-void launch_identify_tile_ranges(int R, const uint16_t* keys, uint2* ranges, cudaStream_t stream) {
-    identify_tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, keys, ranges);
+void launch_identify_tile_ranges(int R, const uint32_t* R_dev, const uint16_t* keys, uint2* ranges, cudaStream_t stream) {
+    identify_tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, R_dev, keys, ranges);
 }
+
+bool radix_lookback_enabled() { return use_lookback(); }
 
 }  // namespace mrgs

@@ -50,10 +50,13 @@ int offsets_in_order(const uint32_t* order, const uint32_t* tiles_touched, int P
                      uint32_t* offsets_incl, cudaStream_t stream);
 void launch_emit_instances(int P, const uint32_t* order, const uint32_t* tiles_touched, const uint2* rect,
                            const uint32_t* offsets_incl, uint16_t* keys, uint32_t* values, int grid_x,
-                           cudaStream_t stream);
+                           uint32_t capacity, cudaStream_t stream);
+// R_dev != nullptr: R is only a capacity (grids, scratch); the kernels read the real count from *R_dev
 int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* vals_b, int R, int tile_bits,
-              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches);
-void launch_identify_tile_ranges(int R, const uint16_t* keys, uint2* ranges, cudaStream_t stream);
+              uint32_t* block_hist, cudaStream_t stream, uint16_t** keys_sorted, uint32_t** vals_sorted, int* launches,
+              const uint32_t* R_dev);
+void launch_identify_tile_ranges(int R, const uint32_t* R_dev, const uint16_t* keys, uint2* ranges, cudaStream_t stream);
+bool radix_lookback_enabled();
 
 // ---- tile blend ----------------------------------------------------------------------------
 struct RenderFwdParams {

@@ -11,6 +11,7 @@ and S > 24 raises instead of silently overflowing MAX_FEATURES.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import NamedTuple
 
 import torch
@@ -57,6 +58,11 @@ class ForwardState(NamedTuple):
     geom: torch.Tensor
     binning: torch.Tensor
     image: torch.Tensor
+
+
+# per-device instance capacity for the optimistic binning buffer: 1.25 x the largest R seen so far
+_capacity_hint = {}
+_OPTIMISTIC = os.environ.get("MRGS_OPTIMISTIC_BINNING", "1") != "0"
 
 
 def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scales, rotations,
@@ -122,14 +128,28 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
     a.image_buffer, a.image_bytes = image.data_ptr(), image.numel()
     cb = _lib.alloc_fn(_alloc)
     a.binning_alloc, a.binning_ctx = cb, None
+    # optimistic binning: lend a buffer sized from the instance counts seen so far on this device, so the
+    # library can enqueue the whole forward before it waits for R (include/mrgs.h, MrgsForwardArgs)
+    scratch = None
+    cap = _capacity_hint.get(dev.index, 0) if _OPTIMISTIC else 0
+    if cap > 0:
+        scratch = torch.empty(lib.mrgs_binning_bytes(cap), dtype=torch.uint8, device=dev)
+        a.binning_scratch, a.binning_scratch_bytes, a.binning_capacity = scratch.data_ptr(), scratch.numel(), cap
 
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.mrgs_forward(C.byref(a), C.c_void_p(stream)), "mrgs_forward")
+    R = int(a.num_rendered)
     binning = holder.get("t")
     if binning is None:
-        binning = torch.empty(0, dtype=torch.uint8, device=dev)
-    return int(a.num_rendered), contrib, color, feature, others, radii, geom, binning, image
+        binning = scratch if (scratch is not None and a.binning_buffer == scratch.data_ptr()) else \
+            torch.empty(0, dtype=torch.uint8, device=dev)
+    binning.mrgs_capacity = int(a.binning_capacity_used)   # layout key for the debug decoders
+    if _OPTIMISTIC:
+        want = (R + R // 4 + 65535) & ~65535
+        if want > cap:
+            _capacity_hint[dev.index] = want
+    return R, contrib, color, feature, others, radii, geom, binning, image
 
 
 def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales, rotations,

@@ -122,7 +122,7 @@ def decode_mrgs_binning(binning: torch.Tensor, R: int, depths: torch.Tensor = No
     from materialrefgs_b200 import _lib
     lib = _lib.load()
     bl = _lib.BinningLayout()
-    assert lib.mrgs_binning_layout(R, C.byref(bl)) == 0
+    assert lib.mrgs_binning_layout(int(getattr(binning, "mrgs_capacity", 0)) or R, C.byref(bl)) == 0
     point_list = binning[bl.point_list:bl.point_list + 4 * R].view(torch.int32)
     tiles = binning[bl.keys:bl.keys + 2 * R].view(torch.int16).to(torch.int64) & 0xffff
     out = {"point_list": point_list, "tile_ids": tiles}

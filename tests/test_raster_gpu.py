@@ -196,6 +196,50 @@ def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
         assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
 
 
+def test_optimistic_binning_paths_are_identical():
+    """MrgsForwardArgs.binning_capacity: the forward enqueued ahead of the R read-back (capacity large
+    enough), its redo when the lent buffer turns out too small, and the exact path must agree bit for bit."""
+    import materialrefgs_b200.rasterizer as raw
+    dev = torch.device("cuda:0")
+    P, S, W, H = 60_000, 8, 640, 480
+    cloud, cam, _ = _scene(P, S, W, H)
+    bg = torch.tensor([0.2, 0.4, 0.6], device=dev)
+    e = torch.empty(0, device=dev)
+    args = (bg, cloud.means3D, e, cloud.features, cloud.opacities, cloud.scales, cloud.rotations, 1.0, e,
+            cam.world_view_transform, cam.full_proj_transform, cam.tanfovx, cam.tanfovy, H, W, cloud.shs, 3,
+            cam.camera_center, False, False)
+    saved = dict(raw._capacity_hint)
+    try:
+        outs = {}
+        raw._capacity_hint.clear()
+        outs["exact"] = raw.rasterize_forward_raw(*args)
+        R = outs["exact"][0]
+        assert outs["exact"][7].mrgs_capacity == R
+        raw._capacity_hint[0] = max(R // 3, 1)
+        outs["redo"] = raw.rasterize_forward_raw(*args)
+        assert outs["redo"][7].mrgs_capacity == R and raw._capacity_hint[0] >= R
+        cap = raw._capacity_hint[0]
+        outs["ahead"] = raw.rasterize_forward_raw(*args)
+        assert outs["ahead"][7].mrgs_capacity == cap
+        raw._capacity_hint[0] = R                      # exactly full
+        outs["tight"] = raw.rasterize_forward_raw(*args)
+        torch.cuda.synchronize()
+        ref = outs["exact"]
+        bref = refimpl.decode_mrgs_binning(ref[7], R)
+        iref = refimpl.decode_mrgs_image(ref[8], H, W)
+        for name, o in outs.items():
+            assert o[0] == R, name
+            for i in (2, 3, 4, 5):
+                assert torch.equal(o[i], ref[i]), (name, i)
+            b = refimpl.decode_mrgs_binning(o[7], R)
+            assert torch.equal(b["point_list"], bref["point_list"]) and torch.equal(b["tile_ids"], bref["tile_ids"]), name
+            im = refimpl.decode_mrgs_image(o[8], H, W)
+            assert torch.equal(im["ranges"], iref["ranges"]) and torch.equal(im["n_contrib"], iref["n_contrib"]), name
+    finally:
+        raw._capacity_hint.clear()
+        raw._capacity_hint.update(saved)
+
+
 def test_c5_scale_view_batch_step_vs_reference(ref_ext):
     """BASELINE config C5 on one rank: 5 M surfels, a view batch run through
     parallel.train_step_view_sharded with the parameters' .grad bound to the gradient arena. The

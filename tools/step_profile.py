@@ -41,3 +41,10 @@ for e in ev:
     agg[k][1] += 1
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][0])[:30]:
     print(f"{v[0] / N:9.1f} us/step {v[1] / N:5.1f}x  {k}")
+# ordered kernel list of the last view of the last step (names shortened), to see the torch glue
+import re
+last_fwd = max(i for i, e in enumerate(ev) if "preprocess_fwd" in e.name)
+print("---- ordered kernels of the last view ----")
+for e in ev[last_fwd - 3:]:
+    nm = re.sub(r"void |at::native::|\(anonymous namespace\)::|mrgs::", "", e.name)[:110]
+    print(f"{e.time_range.elapsed_us():8.1f} us  {nm}")
