@@ -328,6 +328,31 @@ MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
 MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
                       const float* projmatrix, uint8_t* present, void* stream);
 
+/* Per-surfel feature preparation in front of the rasterizer, replacing the ~20 eager
+ * torch kernels of gaussian_renderer/__init__.py:259-266, :334-353 with scene/gaussian_model.py:236-303:
+ *   scales    = exp(scaling)                                   [P,2]
+ *   rotations = rotation / max(|rotation|, 1e-12)              [P,4]
+ *   opacities = sigmoid(opacity)                               [P,1]
+ *   features  = ( sigmoid(refl_strength), sigmoid(roughness), sigmoid(ori_color)[3],
+ *                 clamp_min(eval_sh(3, cat(indirect_dc, indirect_rest), reflection), 0)[3] )   [P,8]
+ * with reflection = 2 (n.w_o) n - w_o, w_o = -(xyz - campos)/|.|, n = the surfel normal (third column of
+ * R(rotation/|rotation|)) flipped towards the camera (flip_align_view) and safe-normalised.
+ * The backward takes the gradients of the four outputs and writes those of the nine raw parameters
+ * (every element is written). All pointers are device pointers of contiguous fp32; campos is [3];
+ * indirect_dc is [P,1,3], indirect_rest [P,15,3]. The forward ignores the dL_* members. */
+typedef struct MrgsSurfelFeatureArgs {
+    int32_t P;
+    const float* campos;
+    const float *xyz, *scaling, *rotation, *opacity, *refl_strength, *roughness, *ori_color, *indirect_dc,
+        *indirect_rest;
+    float *scales, *rotations, *opacities, *features;                                  /* forward outputs  */
+    const float *dL_dscales, *dL_drotations, *dL_dopacities, *dL_dfeatures;            /* backward inputs  */
+    float *dL_dxyz, *dL_dscaling, *dL_drotation, *dL_dopacity, *dL_drefl_strength, *dL_droughness, *dL_dori_color,
+        *dL_dindirect_dc, *dL_dindirect_rest;                                          /* backward outputs */
+} MrgsSurfelFeatureArgs;
+MRGS_API int mrgs_surfel_features_forward(const MrgsSurfelFeatureArgs* args, void* stream);
+MRGS_API int mrgs_surfel_features_backward(const MrgsSurfelFeatureArgs* args, void* stream);
+
 /* Densification statistics of one rendered view, one fused pass over the P surfels
  * (GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061 and the max_radii2D update
  * train_refnerf.py:1416-1418). For every surfel with radii > 0:

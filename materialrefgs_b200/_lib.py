@@ -94,6 +94,14 @@ class ShadeArgs(C.Structure):
 
 
 # every symbol include/mrgs.h declares: name -> (restype, argtypes)
+class SurfelFeatureArgs(C.Structure):
+    _fields_ = [("P", C.c_int32), ("campos", _fp)] + [(n, _fp) for n in (
+        "xyz", "scaling", "rotation", "opacity", "refl_strength", "roughness", "ori_color", "indirect_dc",
+        "indirect_rest", "scales", "rotations", "opacities", "features", "dL_dscales", "dL_drotations",
+        "dL_dopacities", "dL_dfeatures", "dL_dxyz", "dL_dscaling", "dL_drotation", "dL_dopacity",
+        "dL_drefl_strength", "dL_droughness", "dL_dori_color", "dL_dindirect_dc", "dL_dindirect_rest")]
+
+
 SYMBOLS = {
     "mrgs_abi_version": (C.c_int, []),
     "mrgs_last_error": (C.c_char_p, []),
@@ -127,6 +135,8 @@ SYMBOLS = {
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_surfel_features_forward": (C.c_int, [C.POINTER(SurfelFeatureArgs), C.c_void_p]),
+    "mrgs_surfel_features_backward": (C.c_int, [C.POINTER(SurfelFeatureArgs), C.c_void_p]),
     "mrgs_densify_stats": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 

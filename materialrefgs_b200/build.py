@@ -31,6 +31,7 @@ SOURCES = [
     "preprocess_bwd.cu",
     "shade.cu",
     "cubemap.cu",
+    "features.cu",
 ]
 
 NVCC_FLAGS = [

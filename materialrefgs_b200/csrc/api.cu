@@ -229,6 +229,22 @@ __global__ void densify_stats_kernel(int P, const float* __restrict__ g, const i
 }
 }  // namespace
 
+int mrgs_surfel_features_forward(const MrgsSurfelFeatureArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int st = launch_surfel_features(a, false, stream);
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("surfel_features_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_surfel_features_backward(const MrgsSurfelFeatureArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const int st = launch_surfel_features(a, true, stream);
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("surfel_features_bwd", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_densify_stats(int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
                        int32_t* max_radii, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -119,6 +119,7 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 
 // ---- deferred shading ------------------------------------------------------------------------
 int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream);
+int launch_surfel_features(const MrgsSurfelFeatureArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream);
 

@@ -4,7 +4,8 @@ running the rasterizer, the deferred shading and the depth->normal regularisers 
 `pc` is duck-typed like scene/gaussian_model.py's GaussianModel (get_xyz, get_opacity, get_refl,
 get_ori_color, get_rough, get_scaling, get_rotation, get_features, get_indirect, get_normal(), get_envmap,
 active_sh_degree, max_sh_degree); `viewpoint_camera` like scene/cameras.py's Camera; `pipe` needs `debug`
-and `depth_ratio`. The per-surfel feature preparation (:259-353) is still plain torch here.
+and `depth_ratio`. When `pc` exposes the raw parameters (`_scaling`, `_rotation`, ... like GaussianModel) the
+per-surfel feature preparation (:259-353) runs as one libmrgs kernel pair (features.py).
 Unsupported reference branches raise: pipe.compute_cov3D_python, pipe.use_asg, opt.indirect (OptiX/mesh
 visibility tracing stays on the reference).
 """
@@ -15,6 +16,7 @@ import math
 import torch
 
 from .diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+from .features import MODEL_RAW_ATTRS, surfel_features_from_model
 from .shading import shade_surfel, surf_depth_normal
 
 _C0 = 0.28209479177387814
@@ -71,19 +73,24 @@ def render_surfel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_mo
 
     shs, colors_precomp = (pc.get_features, None) if override_color is None else (None, override_color)
 
-    # indirect light: degree-3 SH of the per-surfel reflection direction (:334-345)
-    dir_pp = means3D - viewpoint_camera.camera_center
-    dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
-    normals = pc.get_normal(scaling_modifier, dir_pp_normalized)
-    w_o = -dir_pp_normalized
-    reflection = 2 * torch.sum(normals * w_o, dim=1, keepdim=True) * normals - w_o
-    shs_indirect = pc.get_indirect.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
-    indirect = torch.clamp_min(eval_sh(3, shs_indirect, reflection), 0.0)
-    features = torch.cat((pc.get_refl, pc.get_rough, pc.get_ori_color, indirect), dim=-1)
+    if all(hasattr(pc, n) for n in MODEL_RAW_ATTRS) and pc.max_sh_degree == 3:
+        # a GaussianModel: activations, normal, reflection, indirect SH and the cat as one kernel pair
+        scales, rotations, opacity, features = surfel_features_from_model(pc, viewpoint_camera.camera_center)
+    else:
+        # duck-typed model exposing only the activated getters: the reference's torch lines (:334-353)
+        dir_pp = means3D - viewpoint_camera.camera_center
+        dir_pp_normalized = dir_pp / dir_pp.norm(dim=1, keepdim=True)
+        normals = pc.get_normal(scaling_modifier, dir_pp_normalized)
+        w_o = -dir_pp_normalized
+        reflection = 2 * torch.sum(normals * w_o, dim=1, keepdim=True) * normals - w_o
+        shs_indirect = pc.get_indirect.transpose(1, 2).view(-1, 3, (pc.max_sh_degree + 1) ** 2)
+        indirect = torch.clamp_min(eval_sh(3, shs_indirect, reflection), 0.0)
+        features = torch.cat((pc.get_refl, pc.get_rough, pc.get_ori_color, indirect), dim=-1)
+        scales, rotations, opacity = pc.get_scaling, pc.get_rotation, pc.get_opacity
 
     contrib, rendered_image, rendered_features, radii, allmap = rasterizer(
         means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, features=features,
-        opacities=pc.get_opacity, scales=pc.get_scaling, rotations=pc.get_rotation, cov3D_precomp=None)
+        opacities=opacity, scales=scales, rotations=rotations, cov3D_precomp=None)
 
     surf_depth, surf_normal = surf_depth_normal(allmap, imH, imW, tanfovx, tanfovy, viewpoint_camera.R,
                                                 viewpoint_camera.T, getattr(pipe, "depth_ratio", 0.0))

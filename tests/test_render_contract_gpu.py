@@ -124,3 +124,75 @@ def test_render_surfel_contract(ref_ext):
     close(g_env, env.base.grad, "envmap")
     vis = out["visibility_filter"]
     assert out["viewspace_points"].grad is not None and out["viewspace_points"].grad[vis].abs().sum() > 0
+
+
+class RawModel:
+    """A GaussianModel-like object holding RAW parameters (scene/gaussian_model.py attribute names): render_surfel
+    then prepares the rasterizer inputs with the fused feature kernel."""
+    active_sh_degree = 3
+    max_sh_degree = 3
+
+    def __init__(self, cloud, env, seed=5):
+        from oracle import features_oracle as fo
+        raw, _ = fo.synthetic_params(cloud.P, seed=seed)
+        dev = cloud.means3D.device
+        raw["xyz"] = cloud.means3D.cpu()
+        raw["scaling"] = torch.log(cloud.scales.cpu())
+        raw["rotation"] = cloud.rotations.cpu() * 1.7           # un-normalised on purpose
+        raw["opacity"] = torch.logit(cloud.opacities.cpu().clamp(1e-4, 1 - 1e-4))
+        self.raw = {k: v.to(dev).requires_grad_(True) for k, v in raw.items()}
+        self.shs = cloud.shs.clone().requires_grad_(True)
+        self.env = env
+        r = self.raw
+        self._xyz, self._scaling, self._rotation, self._opacity = r["xyz"], r["scaling"], r["rotation"], r["opacity"]
+        self._refl_strength, self._roughness, self._ori_color = r["refl_strength"], r["roughness"], r["ori_color"]
+        self._indirect_dc, self._indirect_rest = r["indirect_dc"], r["indirect_rest"]
+
+    get_xyz = property(lambda s: s._xyz)
+    get_features = property(lambda s: s.shs)
+    get_envmap = property(lambda s: s.env)
+
+
+def test_render_surfel_contract_raw_parameters(ref_ext):
+    """render_surfel on a raw-parameter model (fused feature preparation + rasterizer + shading + depth normals)
+    against: features oracle -> reference rasterizer -> shading oracle; gradients w.r.t. the RAW parameters."""
+    from materialrefgs_b200.shading import EnvLight
+    from oracle import features_oracle as fo
+    W, H, P = 320, 240, 40_000
+    cloud = synthetic.make_cloud(P, S=8, seed=33).to(DEV)
+    cam = synthetic.orbit_camera(5, 8, W, H).to(DEV)
+    env = EnvLight(device=DEV, max_res=64, min_res=16, trainable=False)
+    with torch.no_grad():
+        env.base.copy_(torch.randn(6, 64, 64, 3, generator=torch.Generator().manual_seed(3)).to(DEV))
+    env.build_mips()
+    pipe = types.SimpleNamespace(debug=False, depth_ratio=0.0, compute_cov3D_python=False, use_asg=False)
+    bg = torch.tensor([0.1, 0.1, 0.1], device=DEV)
+    g = torch.Generator().manual_seed(13)
+    wts = {k: (torch.randn(c, H, W, generator=g) / (H * W)).to(DEV)
+           for k, c in (("render", 3), ("rend_normal", 3), ("surf_normal", 3), ("rend_alpha", 1))}
+    loss_of = lambda o: sum((o[k] * w).sum() for k, w in wts.items())
+
+    pc = RawModel(cloud, env)
+    out = render_surfel(cam, pc, pipe, bg)
+    loss_of(out).backward()
+
+    pc2 = RawModel(cloud, env)
+    scales, rots, opac, feats = fo.prepare_features(*[pc2.raw[k] for k, _ in fo.RAW_FIELDS], cam.camera_center)
+    m2d = torch.zeros_like(pc2._xyz, requires_grad=True)
+    rs = ref_ext.GaussianRasterizationSettings(
+        H, W, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), torch.zeros_like(bg), 1.0,
+        cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center, False, False)
+    _, color, feat, radii, allmap = ref_ext.GaussianRasterizer(rs)(
+        means3D=pc2._xyz, means2D=m2d, opacities=opac, shs=pc2.shs, features=feats, scales=scales, rotations=rots)
+    ref = so.shade_surfel(so.EnvLightOracle([l for l in env.specular]), so.load_lut(DEV), color, feat, allmap, cam, bg)
+    ref["surf_depth"], ref["surf_normal"] = so.surf_depth_normal(allmap, cam, pipe.depth_ratio)
+    loss_of(ref).backward()
+
+    assert torch.equal(out["radii"], radii)
+    for k in ("render", "specular_map", "diffuse_map", "rend_normal", "rend_alpha", "surf_depth", "roughness_map"):
+        assert (out[k] - ref[k]).abs().max().item() <= 1e-4, k
+    for k in pc.raw:
+        a, b = pc.raw[k].grad, pc2.raw[k].grad
+        l1 = ((a - b).abs().sum() / b.abs().sum().clamp_min(1e-20)).item()
+        out_frac = ((a - b).abs() > 1e-2 * b.abs().max()).float().mean().item()
+        assert l1 <= 5e-3 and out_frac <= 1e-3, (k, l1, out_frac)
