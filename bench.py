@@ -208,8 +208,9 @@ class OursStep:
         self.zero_grads()
         V = VIEWS_PER_RANK
         total = 0.0
-        view_of = lambda v: ((i * V + v) * self.world + self.rank + i) % len(self.cams)   # + i: every rank cycles through all cameras
-        if e2e:
+        view_at = lambda step, v: ((step * V + v) * self.world + self.rank + step) % len(self.cams)   # + step: every rank cycles through all cameras
+        view_of = lambda v: view_at(i, v)
+        if e2e and getattr(self, "prefetched_step", None) != i:
             self._e2e_prefetch(view_of(0))
         for v in range(V):
             view = view_of(v)
@@ -217,6 +218,9 @@ class OursStep:
                 cam_mats, up = self._e2e_take()
                 if v + 1 < V:
                     self._e2e_prefetch(view_of(v + 1))   # next view's H2D overlaps this view's kernels
+                else:                                    # like a data loader: the next step's first view is in flight
+                    self._e2e_prefetch(view_at(i + 1, 0))
+                    self.prefetched_step = i + 1
             else:
                 c = self.cam_dev[view]
                 cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
