@@ -353,6 +353,20 @@ typedef struct MrgsSurfelFeatureArgs {
 MRGS_API int mrgs_surfel_features_forward(const MrgsSurfelFeatureArgs* args, void* stream);
 MRGS_API int mrgs_surfel_features_backward(const MrgsSurfelFeatureArgs* args, void* stream);
 
+/* Photometric loss terms of calculate_loss (utils/loss_utils.py:155-157) on [C,H,W] images:
+ *   out2[0] = mean |img - gt|                                  (l1_loss, loss_utils.py:22-23)
+ *   out2[1] = mean SSIM map, 11x11 Gaussian window sigma 1.5, zero padding, C1 = 0.01^2, C2 = 0.03^2
+ *             (ssim / _ssim, loss_utils.py:83-119, size_average = True)
+ * forward : `maps` ([3][C][H][W], may be NULL when no gradient is wanted) receives the three per-pixel SSIM
+ *           derivative maps the backward filters; `partials` is scratch of mrgs_photometric_partials_bytes().
+ * backward: upstream = device [2] = (dL/d out2[0], dL/d out2[1]); dimg [C][H][W] is written (gt has no gradient).
+ * Sums are formed in a fixed order (deterministic). */
+MRGS_API size_t mrgs_photometric_partials_bytes(int32_t channels, int32_t height, int32_t width);
+MRGS_API int mrgs_photometric_forward(const float* img, const float* gt, int32_t channels, int32_t height, int32_t width,
+                                      float* maps, float* partials, float* out2, void* stream);
+MRGS_API int mrgs_photometric_backward(const float* img, const float* gt, const float* maps, int32_t channels,
+                                       int32_t height, int32_t width, const float* upstream, float* dimg, void* stream);
+
 /* Densification statistics of one rendered view, one fused pass over the P surfels
  * (GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061 and the max_radii2D update
  * train_refnerf.py:1416-1418). For every surfel with radii > 0:

@@ -137,6 +137,9 @@ SYMBOLS = {
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
     "mrgs_surfel_features_forward": (C.c_int, [C.POINTER(SurfelFeatureArgs), C.c_void_p]),
     "mrgs_surfel_features_backward": (C.c_int, [C.POINTER(SurfelFeatureArgs), C.c_void_p]),
+    "mrgs_photometric_partials_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "mrgs_photometric_forward": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_photometric_backward": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, C.c_void_p]),
     "mrgs_densify_stats": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 

@@ -32,6 +32,7 @@ SOURCES = [
     "shade.cu",
     "cubemap.cu",
     "features.cu",
+    "losses.cu",
 ]
 
 NVCC_FLAGS = [

@@ -245,6 +245,35 @@ int mrgs_surfel_features_backward(const MrgsSurfelFeatureArgs* a, void* stream_)
     return MRGS_OK;
 }
 
+size_t mrgs_photometric_partials_bytes(int32_t C, int32_t H, int32_t W) {
+    if (C <= 0 || H <= 0 || W <= 0) return 0;
+    return photometric_partials_count(C, H, W) * sizeof(float2);
+}
+
+int mrgs_photometric_forward(const float* img, const float* gt, int32_t C, int32_t H, int32_t W, float* maps,
+                             float* partials, float* out2, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535 || !img || !gt || !partials || !out2) {
+        set_error("mrgs_photometric_forward: bad arguments (C=%d H=%d W=%d)", C, H, W);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    launch_photometric_fwd(img, gt, C, H, W, maps, partials, out2, stream);
+    MRGS_LAUNCH_OK("photometric_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_photometric_backward(const float* img, const float* gt, const float* maps, int32_t C, int32_t H, int32_t W,
+                              const float* upstream, float* dimg, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535 || !img || !gt || !maps || !upstream || !dimg) {
+        set_error("mrgs_photometric_backward: bad arguments (C=%d H=%d W=%d)", C, H, W);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    launch_photometric_bwd(img, gt, maps, C, H, W, upstream, dimg, stream);
+    MRGS_LAUNCH_OK("photometric_bwd", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_densify_stats(int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
                        int32_t* max_radii, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -119,6 +119,11 @@ void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream);
 
 // ---- deferred shading ------------------------------------------------------------------------
 int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream);
+size_t photometric_partials_count(int C, int H, int W);
+int launch_photometric_fwd(const float* img, const float* gt, int C, int H, int W, float* maps, float* partials,
+                           float* out2, cudaStream_t stream);
+int launch_photometric_bwd(const float* img, const float* gt, const float* maps, int C, int H, int W,
+                           const float* upstream, float* dimg, cudaStream_t stream);
 int launch_surfel_features(const MrgsSurfelFeatureArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream);
