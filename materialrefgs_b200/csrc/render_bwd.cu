@@ -102,16 +102,15 @@ render_bwd_kernel(const RenderBwdParams p) {
         dL_dreg = p.dL_dothers[kDistortionOff * HW + pix];
     }
 
+    // Blend recurrences in closed form. The reference walks back to front keeping, per channel, the colour
+    // accumulated BEHIND the current surfel (accum_rec) and adds (c - accum_rec) * dL_dpixel * T to dL_dalpha.
+    // With q_i = sum over ALL blended channels of value_i * dL_dchannel (colour, features, depth, normal, alpha)
+    // and w_k = alpha_k T_k this is   T_i q_i - B_i / (1 - alpha_i),   B_i = sum_{k behind i} w_k q_k :
+    // one dot product per pair and ONE scalar running sum instead of 2 vectors of per-channel state
+    // (gradient-only arithmetic: every skip decision stays exact, the 1e-3 bar is checked by the parity tests).
     float T = T_final;
-    float last_alpha = 0.f;
-    float2 accum_rec[NC / 2], last_val[NC / 2];
-#pragma unroll
-    for (int c = 0; c < NC / 2; ++c) {
-        accum_rec[c] = make_float2(0.f, 0.f);
-        last_val[c] = make_float2(0.f, 0.f);
-    }
-    float last_depth = 0.f, accum_depth_rec = 0.f, accum_alpha_rec = 0.f, last_dL_dT = 0.f;
-    float ln0 = 0.f, ln1 = 0.f, ln2 = 0.f, an0 = 0.f, an1 = 0.f, an2 = 0.f;
+    float behind = 0.f;       // B
+    float last_dL_dT = 0.f;
 
     const float4* __restrict__ rec4 = reinterpret_cast<const float4*>(p.rec);
     const float4* __restrict__ cf4 = reinterpret_cast<const float4*>(p.cf);
@@ -170,31 +169,23 @@ render_bwd_kernel(const RenderBwdParams p) {
                 const float inv_1ma = __fdividef(1.0f, 1.0f - alpha);
                 T = T * inv_1ma;
                 const float w = alpha * T;
-                float dL_dalpha = 0.0f;
+                float q;
                 {
-                    // the per-channel recurrences run two channels per instruction (Blackwell packed fp32:
-                    // fma.rn.f32x2 / mul.rn.f32x2) — the kernel is issue bound, not FMA-pipe bound
-                    const float2 la2 = make_float2(last_alpha, last_alpha);
-                    const float2 oml2 = make_float2(1.0f - last_alpha, 1.0f - last_alpha);
+                    // two channels per instruction (Blackwell packed fp32: fma.rn.f32x2 / mul.rn.f32x2)
                     const float2 w2 = make_float2(w, w);
-                    const float2 neg1 = make_float2(-1.0f, -1.0f);
-                    float2 dsum = make_float2(0.0f, 0.0f);
+                    float2 dot2 = make_float2(0.0f, 0.0f);
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const float4 cv = s_cf[warp][q][j];
-                        const float2 cc[2] = {make_float2(cv.x, cv.y), make_float2(cv.z, cv.w)};
-#pragma unroll
-                        for (int k = 0; k < 2; ++k) {
-                            const int c = 2 * q + k;
-                            accum_rec[c] = __ffma2_rn(la2, last_val[c], __fmul2_rn(oml2, accum_rec[c]));
-                            last_val[c] = cc[k];
-                            dsum = __ffma2_rn(__ffma2_rn(accum_rec[c], neg1, cc[k]), dL_dpix[c], dsum);
-                            const float2 gcf = __fmul2_rn(w2, dL_dpix[c]);
-                            v[kGradColor + 2 * c] = gcf.x;
-                            v[kGradColor + 2 * c + 1] = gcf.y;
-                        }
+                    for (int k = 0; k < NQ; ++k) {
+                        const float4 cv = s_cf[warp][k][j];
+                        dot2 = __ffma2_rn(make_float2(cv.x, cv.y), dL_dpix[2 * k], dot2);
+                        dot2 = __ffma2_rn(make_float2(cv.z, cv.w), dL_dpix[2 * k + 1], dot2);
+                        const float2 ga = __fmul2_rn(w2, dL_dpix[2 * k]), gb = __fmul2_rn(w2, dL_dpix[2 * k + 1]);
+                        v[kGradColor + 4 * k + 0] = ga.x;
+                        v[kGradColor + 4 * k + 1] = ga.y;
+                        v[kGradColor + 4 * k + 2] = gb.x;
+                        v[kGradColor + 4 * k + 3] = gb.y;
                     }
-                    dL_dalpha = dsum.x + dsum.y;
+                    q = dot2.x + dot2.y;
                 }
 
                 const float c_d = h.depth;
@@ -203,30 +194,19 @@ render_bwd_kernel(const RenderBwdParams p) {
                 float dL_dz = 0.0f;
                 if (e == median_contributor - 1) dL_dz += dL_dmedian;
                 const float dL_dweight = (final_D2 + m_d * m_d * final_A - 2.0f * m_d * final_D) * dL_dreg;
-                dL_dalpha += dL_dweight - last_dL_dT;
+                const float dist_term = dL_dweight - last_dL_dT;
                 last_dL_dT = dL_dweight * alpha + (1.0f - alpha) * last_dL_dT;
                 const float dL_dmd = 2.0f * w * (m_d * final_A - final_D) * dL_dreg;
                 dL_dz += dL_dmd * dmd_dd;
 
-                accum_depth_rec = last_alpha * last_depth + (1.0f - last_alpha) * accum_depth_rec;
-                last_depth = c_d;
-                dL_dalpha += (c_d - accum_depth_rec) * dL_ddepth;
-                accum_alpha_rec = last_alpha + (1.0f - last_alpha) * accum_alpha_rec;
-                dL_dalpha += (1.0f - accum_alpha_rec) * dL_daccum;
-
-                an0 = last_alpha * ln0 + (1.0f - last_alpha) * an0;
-                an1 = last_alpha * ln1 + (1.0f - last_alpha) * an1;
-                an2 = last_alpha * ln2 + (1.0f - last_alpha) * an2;
-                ln0 = g3.x;
-                ln1 = g3.y;
-                ln2 = g3.z;
-                dL_dalpha += (g3.x - an0) * dL_dn0 + (g3.y - an1) * dL_dn1 + (g3.z - an2) * dL_dn2;
+                // depth, alpha ("colour" 1) and normal are blended channels like the colours
+                q += c_d * dL_ddepth + dL_daccum + g3.x * dL_dn0 + g3.y * dL_dn1 + g3.z * dL_dn2;
                 v[kGradNormal + 0] = w * dL_dn0;
                 v[kGradNormal + 1] = w * dL_dn1;
                 v[kGradNormal + 2] = w * dL_dn2;
 
-                dL_dalpha *= T;
-                last_alpha = alpha;
+                float dL_dalpha = T * (q + dist_term) - inv_1ma * behind;
+                behind += w * q;
                 if (bg_dot_dpixel != 0.0f) dL_dalpha += (-T_final * inv_1ma) * bg_dot_dpixel;
 
                 const float dL_dG = g2.w * dL_dalpha;
