@@ -82,8 +82,9 @@ typedef struct MrgsGeomLayout {
     size_t point_offsets; /* uint32[P] inclusive prefix sum of tiles_touched IN DEPTH-SORTED surfel order    */
     size_t rect;          /* uint32[P][2]: (min.x | min.y<<16), (max.x | max.y<<16) tile rectangle        */
     size_t depth;         /* float [P]: view-space depth p_view.z (the low 32 key bits)                   */
-    size_t bbox;          /* float [P][4]: conservative pixel bounds (xmin,ymin,xmax,ymax) of the region
-                             where the surfel's alpha can reach 1/255; used for per-warp culling          */
+    size_t bbox;          /* float [P][8]: conservative pixel bounds of the region where the surfel's alpha can
+                             reach 1/255, as an octagon: (xmin,ymin,xmax,ymax) then (umin,vmin,umax,vmax) with
+                             u = x+y, v = x-y; used for per-warp culling                                    */
     size_t sort_keys;     /* uint32[2][P] ping-pong depth keys (depth bits, 0xffffffff = culled)          */
     size_t sort_vals;     /* uint32[2][P] ping-pong surfel ids; [0] ends up holding the depth order       */
     size_t scan_temp;     /* radix-pass histograms / scan block sums                                      */

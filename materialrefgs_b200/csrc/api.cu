@@ -145,7 +145,7 @@ int mrgs_geom_layout(int32_t P, int32_t S, MrgsGeomLayout* out) {
     out->point_offsets = off; off = align_up(off + n * sizeof(uint32_t));
     out->rect = off;          off = align_up(off + n * sizeof(uint2));
     out->depth = off;         off = align_up(off + n * sizeof(float));
-    out->bbox = off;          off = align_up(off + n * sizeof(float4));
+    out->bbox = off;          off = align_up(off + 2 * n * sizeof(float4));
     out->sort_keys = off;     off = align_up(off + 2 * n * sizeof(uint32_t));
     out->sort_vals = off;     off = align_up(off + 2 * n * sizeof(uint32_t));
     out->scan_temp = off;

@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
 
     const float opacity = p.opacities[idx];
     float tau;
-    const float4 bb = alpha_support_bounds(T, cx, cy, opacity, tau);
+    float4 bd;
+    const float4 bb = alpha_support_bounds(T, cx, cy, opacity, tau, bd);
 
     float4* rec = reinterpret_cast<float4*>(p.rec + (size_t)idx * kGeomFloats);
     rec[0] = make_float4(T[0], T[1], T[2], T[6]);
@@ -192,7 +193,8 @@ __global__ void __launch_bounds__(256) preprocess_fwd_kernel(PreprocessParams p)
     rec[3] = make_float4(normal.x, normal.y, normal.z, tau);
     p.depth[idx] = pv.z;
     p.sort_key[idx] = __float_as_uint(pv.z);
-    p.bbox[idx] = bb;
+    p.bbox[2 * idx] = bb;       // one 32-byte sector per surfel: box, then the diagonal slabs
+    p.bbox[2 * idx + 1] = bd;
 
     p.rect[idx] = make_uint2((unsigned)x0 | ((unsigned)y0 << 16), (unsigned)x1 | ((unsigned)y1 << 16));
     p.radii[idx] = radius;

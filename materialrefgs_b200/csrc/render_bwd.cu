@@ -56,6 +56,7 @@ render_bwd_kernel(const RenderBwdParams p) {
     const size_t pix = (size_t)py * p.W + px;
     const float bx0 = (float)(blockIdx.x * kTileX + (warp & 1) * 8), bx1 = bx0 + 7.0f;
     const float by0 = (float)(blockIdx.y * kTileY + (warp >> 1) * 4), by1 = by0 + 3.0f;
+    const float bu0 = bx0 + by0, bu1 = bx1 + by1, bv0 = bx0 - by1, bv1 = bx1 - by0;  // diagonal extents
 
     const uint2 range = p.ranges[tile];
     const uint32_t* __restrict__ list = p.point_list + range.x;
@@ -118,22 +119,25 @@ render_bwd_kernel(const RenderBwdParams p) {
     // back-to-front in steps of 32 list entries; lane l of a step holds entry hi-1-l, so walking the
     // survivor mask from bit 0 upwards visits entries in descending order
     uint32_t id_next = 0;
-    float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f);
+    float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f), bd_next = bb_next;
     if (warp_last - 1 - lane >= 0) {
         id_next = list[warp_last - 1 - lane];
-        bb_next = p.bbox[id_next];
+        bb_next = p.bbox[2 * id_next];
+        bd_next = p.bbox[2 * id_next + 1];
     }
 
     for (int hi = warp_last; hi > 0; hi -= 32) {
         const uint32_t id = id_next;
-        const float4 bb = bb_next;
+        const float4 bb = bb_next, bd = bd_next;
         const int e_mine = hi - 1 - lane;
         const int e_next = e_mine - 32;
         if (e_next >= 0) {
             id_next = list[e_next];
-            bb_next = p.bbox[id_next];
+            bb_next = p.bbox[2 * id_next];
+            bd_next = p.bbox[2 * id_next + 1];
         }
-        const bool keep = (e_mine >= 0) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0);
+        const bool keep = (e_mine >= 0) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0) &&
+                          !(bd.x > bu1 || bd.z < bu0 || bd.y > bv1 || bd.w < bv0);
         unsigned mask = __ballot_sync(kFull, keep);
         if (mask == 0) continue;
         if (keep) {

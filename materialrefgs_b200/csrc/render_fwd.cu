@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
     float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f);
     if (lane < count) {
         id_next = list[lane];
-        bb_next = p.bbox[id_next];
+        bb_next = p.bbox[2 * id_next];
     }
 
     for (int base = 0; base < count; base += 32) {
@@ -74,8 +74,10 @@ __global__ void __launch_bounds__(kTilePixels) render_fwd_kernel(const RenderFwd
         const int e_next = base + 32 + lane;
         if (e_next < count) {
             id_next = list[e_next];
-            bb_next = p.bbox[id_next];
+            bb_next = p.bbox[2 * id_next];
         }
+        // (the backward also tests the diagonal slabs stored next to the box; measured here the extra
+        // gather costs the forward more than the pairs it removes: 0.458 -> 0.469 ms)
         const bool keep = (base + lane < count) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0);
         unsigned mask = __ballot_sync(kFullMask, keep);
         if (mask == 0) continue;

@@ -162,24 +162,35 @@ __device__ __forceinline__ void tile_rect(float cx, float cy, int radius, int gr
 // compute_aabb formula with cutoff^2 = tau instead of 9) united with {rho2d <= tau} (disc of radius
 // sqrt(tau/2) around the 3-sigma centre), inflated by half a pixel. Surfels whose tau-ellipse reaches
 // the camera plane (unbounded projection) or whose box is numerically doubtful are never culled.
+// `diag` receives the same kind of bound along the two diagonals, (umin, vmin, umax, vmax) with u = x + y and
+// v = x - y: together with the box it is an octagon (8-DOP) around the support region, which for thin surfels
+// lying diagonally on screen is far tighter than the box alone. The extent of the projected ellipse along
+// any screen direction n follows from the same formula with the row n.x * T[0..2] + n.y * T[3..5].
 __device__ __forceinline__ float4 alpha_support_bounds(const float* T, float cx, float cy, float opacity,
-                                                       float& tau) {
+                                                       float& tau, float4& diag) {
     const float inf = __int_as_float(0x7f800000);
+    const float4 everything = make_float4(-inf, -inf, inf, inf);
+    const float4 nothing = make_float4(inf, inf, -inf, -inf);
+    diag = everything;
     tau = 2.0f * logf(255.0f * opacity) * 1.001f + 0.001f;
     if (!(tau > 0.0f)) {  // opacity < 1/255 (or NaN): alpha can never reach 1/255
         if (!(tau <= 0.0f)) tau = inf;  // NaN opacity: disable every shortcut
-        return (tau == inf) ? make_float4(-inf, -inf, inf, inf) : make_float4(inf, inf, -inf, -inf);
+        if (tau != inf) diag = nothing;
+        return (tau == inf) ? everything : nothing;
     }
-    const float4 everything = make_float4(-inf, -inf, inf, inf);
     const float t6 = T[6], t7 = T[7], t8 = T[8];
     const float d = tau * (t6 * t6 + t7 * t7) - t8 * t8;
     if (!(d < -1e-4f * t8 * t8)) return everything;
     const float rc = 1.0f / d;
     const float fx = tau * rc, fz = -rc;
-    const float ex_c = fx * (T[0] * t6 + T[1] * t7) + fz * T[2] * t8;
-    const float ey_c = fx * (T[3] * t6 + T[4] * t7) + fz * T[5] * t8;
-    const float hx = ex_c * ex_c - (fx * (T[0] * T[0] + T[1] * T[1]) + fz * T[2] * T[2]);
-    const float hy = ey_c * ey_c - (fx * (T[3] * T[3] + T[4] * T[4]) + fz * T[5] * T[5]);
+    // centre and squared half extent of the tau-ellipse along the screen direction whose T row is (r0, r1, r2)
+    auto extent = [&](float r0, float r1, float r2, float& centre, float& half2) {
+        centre = fx * (r0 * t6 + r1 * t7) + fz * r2 * t8;
+        half2 = centre * centre - (fx * (r0 * r0 + r1 * r1) + fz * r2 * r2);
+    };
+    float ex_c, ey_c, eu_c, ev_c, hx, hy, hu, hv;
+    extent(T[0], T[1], T[2], ex_c, hx);
+    extent(T[3], T[4], T[5], ey_c, hy);
     if (!(hx >= 0.0f) || !(hy >= 0.0f)) return everything;
     const float ex = sqrtf(hx), ey = sqrtf(hy);
     const float rlp = sqrtf(0.5f * tau);
@@ -191,6 +202,21 @@ __device__ __forceinline__ float4 alpha_support_bounds(const float* T, float cx,
     bb.z = fmaxf(ex_c + ex, cx + rlp) + mx;
     bb.w = fmaxf(ey_c + ey, cy + rlp) + my;
     if (!(bb.x <= bb.z) || !(bb.y <= bb.w)) return everything;  // NaN guard
+    extent(T[0] + T[3], T[1] + T[4], T[2] + T[5], eu_c, hu);
+    extent(T[0] - T[3], T[1] - T[4], T[2] - T[5], ev_c, hv);
+    if (hu >= 0.0f && hv >= 0.0f) {
+        const float eu = sqrtf(hu), ev = sqrtf(hv);
+        const float rd = rlp * 1.41421366f;  // the disc's half extent along a (1, +-1) direction, rounded up
+        const float cu = cx + cy, cv = cx - cy;
+        const float mu = 1.0f + 2e-3f * (eu + rd + fabsf(eu_c - cu));
+        const float mv = 1.0f + 2e-3f * (ev + rd + fabsf(ev_c - cv));
+        float4 dd;
+        dd.x = fminf(eu_c - eu, cu - rd) - mu;
+        dd.y = fminf(ev_c - ev, cv - rd) - mv;
+        dd.z = fmaxf(eu_c + eu, cu + rd) + mu;
+        dd.w = fmaxf(ev_c + ev, cv + rd) + mv;
+        if ((dd.x <= dd.z) && (dd.y <= dd.w)) diag = dd;
+    }
     return bb;
 }
 

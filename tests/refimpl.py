@@ -79,7 +79,7 @@ def decode_mrgs_geom(geom: torch.Tensor, P: int, S: int):
         "transMat": torch.cat([rec[:, 0:3], rec[:, 4:7], rec[:, 3:4], rec[:, 7:8], rec[:, 8:9]], 1),
         "means2D": rec[:, 9:11], "opacity": rec[:, 11], "normal": rec[:, 12:15], "tau": rec[:, 15],
         "depths": geom[gl.depth:gl.depth + 4 * P].view(torch.float32),
-        "bbox": geom[gl.bbox:gl.bbox + 16 * P].view(torch.float32).view(P, 4),
+        "bbox": geom[gl.bbox:gl.bbox + 32 * P].view(torch.float32).view(P, 8),
         "rgb": cf[:, 0:3], "features": cf[:, 3:3 + S],
         "clamped": geom[gl.clamped:gl.clamped + P],
         "tiles_touched": geom[gl.tiles_touched:gl.tiles_touched + 4 * P].view(torch.int32),
