@@ -269,13 +269,23 @@ class _RasterizeGaussians(torch.autograd.Function):
         rs = ctx.raster_settings
         (colors_precomp, features, means3D, scales, rotations, cov3Ds_precomp, radii, sh, geom,
          binning, image, contrib) = ctx.saved_tensors
+        args = (rs.bg, means3D, radii, colors_precomp, features, scales, rotations, rs.scale_modifier,
+                cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color,
+                grad_out_feature, grad_depth, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered,
+                binning, image, contrib, rs.debug)
+        want = dict(need_colors=ctx.needs_input_grad[3], need_transmat=ctx.needs_input_grad[8])
+        if rs.debug:  # same failure artefact as the reference (rast/diff_surfel_rasterization/__init__.py:141-148)
+            cpu_args = _cpu_deep_copy_tuple(args)
+            try:
+                grads = rasterize_backward_raw(*args, **want)
+            except Exception as ex:
+                torch.save(cpu_args, "snapshot_bw.dump")
+                print("\nAn error occured in backward. Writing snapshot_bw.dump for debugging.\n")
+                raise ex
+        else:
+            grads = rasterize_backward_raw(*args, **want)
         (grad_means2D, grad_colors_precomp, grad_features, grad_opacities, grad_means3D,
-         grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations) = rasterize_backward_raw(
-            rs.bg, means3D, radii, colors_precomp, features, scales, rotations, rs.scale_modifier,
-            cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color,
-            grad_out_feature, grad_depth, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered,
-            binning, image, contrib, rs.debug, need_colors=ctx.needs_input_grad[3],
-            need_transmat=ctx.needs_input_grad[8])
+         grad_cov3Ds_precomp, grad_sh, grad_scales, grad_rotations) = grads
         if not ctx.needs_input_grad[3]:
             grad_colors_precomp = None
         if not ctx.needs_input_grad[8]:

@@ -27,12 +27,12 @@ def _settings(mod, cam, bg, sh_degree=3, scale_modifier=1.0, debug=False):
         sh_degree=sh_degree, campos=cam.camera_center, prefiltered=False, debug=debug)
 
 
-def _run(mod, cloud, cam, bg, grads, sh_degree=3, scale_modifier=1.0, use_sh=True):
+def _run(mod, cloud, cam, bg, grads, sh_degree=3, scale_modifier=1.0, use_sh=True, debug=False):
     """Forward + backward through the package-level API of `mod` (reference or ours)."""
     leaves = {k: getattr(cloud, k).clone().requires_grad_(True)
               for k in ("means3D", "scales", "rotations", "opacities", "shs", "features")}
     means2D = torch.zeros_like(leaves["means3D"], requires_grad=True)
-    rast = mod.GaussianRasterizer(_settings(mod, cam, bg, sh_degree, scale_modifier))
+    rast = mod.GaussianRasterizer(_settings(mod, cam, bg, sh_degree, scale_modifier, debug))
     colors = None
     if not use_sh:
         colors = (leaves["shs"][:, 0, :] * synthetic.SH_C0 + 0.5)
@@ -194,6 +194,50 @@ def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
     b = _run(ref_ext, cloud, cam, bg, grads)
     for k in a["grads"]:
         assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
+
+
+def test_debug_mode_matches_and_writes_snapshots(tmp_path, monkeypatch):
+    """raster_settings.debug=True: synchronise + check after every launch, identical results; a failing call
+    leaves snapshot_fw.dump / snapshot_bw.dump like the reference (diff_surfel_rasterization/__init__.py:87-94, :141-148)."""
+    import materialrefgs_b200.diff_surfel_rasterization as ours
+    import materialrefgs_b200.rasterizer as raw
+    monkeypatch.chdir(tmp_path)
+    dev = torch.device("cuda:0")
+    cloud, cam, grads = _scene(8_000, 8, 200, 150)
+    bg = torch.zeros(3, device=dev)
+    a = _run(ours, cloud, cam, bg, grads, debug=False)
+    b = _run(ours, cloud, cam, bg, grads, debug=True)
+    for k in ("color", "feature", "allmap", "radii"):
+        assert torch.equal(a[k], b[k]), k
+    for k in a["grads"]:
+        assert _rel_err(b["grads"][k], a["grads"][k]) <= 1e-5, k
+    assert not (tmp_path / "snapshot_fw.dump").exists()
+
+    # forward failure: more feature channels than the library supports
+    wide = torch.zeros(cloud.P, 25, device=dev)
+    rs = _settings(ours, cam, bg, debug=True)
+    with pytest.raises(RuntimeError):
+        ours.GaussianRasterizer(rs)(means3D=cloud.means3D, means2D=None, opacities=cloud.opacities, shs=cloud.shs,
+                                    features=wide, scales=cloud.scales, rotations=cloud.rotations)
+    assert (tmp_path / "snapshot_fw.dump").exists()
+    dumped = torch.load(tmp_path / "snapshot_fw.dump", weights_only=False)
+    assert len(dumped) == 20 and not dumped[1].is_cuda and tuple(dumped[3].shape) == (cloud.P, 25)
+
+    # backward failure (injected): the arguments are dumped before the exception propagates
+    leaves = cloud.means3D.clone().requires_grad_(True)
+    _, color, feat, radii, allmap = ours.GaussianRasterizer(rs)(
+        means3D=leaves, means2D=None, opacities=cloud.opacities, shs=cloud.shs, features=cloud.features,
+        scales=cloud.scales, rotations=cloud.rotations)
+    orig = raw.rasterize_backward_raw
+
+    def broken(*args, **kw):
+        raise RuntimeError("injected backward failure")
+    monkeypatch.setattr(raw, "rasterize_backward_raw", broken)
+    with pytest.raises(RuntimeError):
+        color.sum().backward()
+    monkeypatch.setattr(raw, "rasterize_backward_raw", orig)
+    assert (tmp_path / "snapshot_bw.dump").exists()
+    assert len(torch.load(tmp_path / "snapshot_bw.dump", weights_only=False)) == 25
 
 
 def test_optimistic_binning_paths_are_identical():
