@@ -170,19 +170,17 @@ class OursStep:
         self.cam_dev = [c.to(dev) for c in self.cams]
         self.cam_host = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(),
                           c.camera_center.pin_memory()) for c in self.cams]
-        if world > 1:
-            from materialrefgs_b200.parallel import GradArena
-            self.arena = GradArena.create(WORKLOAD["P"], dev)
-            self.arena.bind(self.leaves)   # .grad of every parameter IS its arena segment
+        # The gradient arena (materialrefgs_b200/parallel.py) is the parameters' .grad AND the rasterizer's
+        # grad_sink: the per-surfel backward adds every view's gradients into it, one allreduce follows (N > 1).
+        from materialrefgs_b200.parallel import GradArena
+        self.arena = GradArena.create(WORKLOAD["P"], dev)
+        self.arena.bind(self.leaves)
+        self.sink = self.arena.views if self.name == "ours" else None
         self.last = {}
 
     def zero_grads(self):
-        if self.world > 1:
-            self.arena.zero_()             # one memset: gradient segments + statistics tail
-            rest = self.levels + [self.means2D]
-        else:
-            rest = list(self.leaves.values()) + self.levels + [self.means2D]
-        for t in rest:
+        self.arena.zero_()                 # one memset: gradient segments + statistics tail
+        for t in self.levels + [self.means2D]:
             t.grad = None
 
     def render(self, view, cam_mats, up):
@@ -191,7 +189,7 @@ class OursStep:
         rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, wvt, proj,
                       WORKLOAD["sh_degree"], center, False, False)
         L = self.leaves
-        contrib, color, feat, radii, allmap = self.GR(rs)(
+        contrib, color, feat, radii, allmap = (self.GR(rs, grad_sink=self.sink) if self.sink is not None else self.GR(rs))(
             means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
             features=L["features"], scales=L["scales"], rotations=L["rotations"])
         out = self.shade(self.env, color, feat, allmap, cam.HWK, cam.R, self.bg)
@@ -313,7 +311,7 @@ class ReferenceStep(OursStep):
         rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, wvt, proj,
                       WORKLOAD["sh_degree"], center, False, False)
         L = self.leaves
-        contrib, color, feat, radii, allmap = self.GR(rs)(
+        contrib, color, feat, radii, allmap = (self.GR(rs, grad_sink=self.sink) if self.sink is not None else self.GR(rs))(
             means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
             features=L["features"], scales=L["scales"], rotations=L["rotations"])
         loss = (color * up["render"]).sum() + (allmap * up["allmap"]).sum() + (feat * self.up_feat).sum()

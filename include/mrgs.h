@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 4
+#define MRGS_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -200,6 +200,11 @@ typedef struct MrgsBackwardArgs {
     float* dL_drotations; /* [P,4]                                                      */
     /* scratch: raw per-surfel gradient arena, >= mrgs_grad_arena_bytes(P,S) */
     void* grad_arena;     size_t grad_arena_bytes;
+    /* != 0: gradient accumulation fused into the per-surfel backward. dL_dmeans3D, dL_dsh, dL_dfeatures,
+     * dL_dopacity, dL_dscales, dL_drotations (and dL_dcolors / dL_dtransMat when given) are ADDED to, rows of
+     * culled surfels are left untouched; dL_dmeans2D (the per-view densification proxy) is still overwritten.
+     * Lets a view batch accumulate straight into the buffer that is all-reduced. Needs M <= 16. */
+    int32_t accumulate;
 } MrgsBackwardArgs;
 
 MRGS_API size_t mrgs_grad_arena_bytes(int32_t P, int32_t S);

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 4
+MRGS_ABI_VERSION = 5
 MAX_FEATURES = 24
 TILE = 16
 
@@ -71,7 +71,7 @@ class BackwardArgs(C.Structure):
         ("dL_dmeans2D", _fp), ("dL_dcolors", _fp), ("dL_dfeatures", _fp), ("dL_dopacity", _fp),
         ("dL_dmeans3D", _fp), ("dL_dtransMat", _fp), ("dL_dsh", _fp), ("dL_dscales", _fp),
         ("dL_drotations", _fp),
-        ("grad_arena", _fp), ("grad_arena_bytes", C.c_size_t),
+        ("grad_arena", _fp), ("grad_arena_bytes", C.c_size_t), ("accumulate", C.c_int32),
     ]
 
 

@@ -762,6 +762,11 @@ int mrgs_backward(const MrgsBackwardArgs* a, void* stream_) {
     PreprocessBwdParams pb{};
     pb.P = a->P; pb.S = a->S; pb.D = a->sh_degree; pb.M = a->sh_coeffs; pb.W = Wb; pb.H = Hb;
     pb.cf_stride = gl.cf_stride; pb.grad_stride = grad_stride(a->S);
+    pb.accumulate = a->accumulate != 0;
+    if (pb.accumulate && a->shs != nullptr && a->sh_coeffs > 16) {
+        set_error("mrgs_backward: accumulate needs sh_coeffs <= 16, got %d", a->sh_coeffs);
+        return MRGS_ERR_UNSUPPORTED;
+    }
     pb.means3D = a->means3D; pb.scales = a->scales; pb.rotations = a->rotations; pb.shs = a->shs;
     pb.transMat_precomp = a->transMat_precomp;
     pb.viewmatrix = a->viewmatrix; pb.projmatrix = a->projmatrix; pb.campos = a->campos;

@@ -93,6 +93,7 @@ int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream);
 struct PreprocessBwdParams {
     int P, S, D, M, W, H;  // W,H here are the reference's recomputed int(focal*tan*2) values
     int cf_stride, grad_stride;
+    int accumulate;  // add to the parameter-gradient outputs instead of overwriting them
     const float* means3D;
     const float* scales;
     const float* rotations;

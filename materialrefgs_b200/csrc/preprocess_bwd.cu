@@ -114,11 +114,31 @@ __device__ __forceinline__ V3 sh_backward(int deg, int M, const float* __restric
     return r;
 }
 
+// kAcc: ADD the parameter gradients to what the output buffers hold (gradient accumulation over the views of a
+// batch fused into this kernel: no separate add pass, no freshly written temporaries) and leave the rows of
+// culled surfels untouched. dL_dmeans2D, the per-view densification proxy, is always overwritten.
+template <bool kAcc> __device__ __forceinline__ void put(float* dst, float v) { *dst = kAcc ? (*dst + v) : v; }
+template <bool kAcc> __device__ __forceinline__ void put(float2* dst, float2 v) {
+    if (kAcc) { const float2 o = *dst; v.x += o.x; v.y += o.y; }
+    *dst = v;
+}
+template <bool kAcc> __device__ __forceinline__ void put(float4* dst, float4 v) {
+    if (kAcc) { const float4 o = *dst; v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w; }
+    *dst = v;
+}
+
+template <bool kAcc>
 __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwdParams p) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= p.P) return;
 
     const bool visible = p.radii[idx] > 0;
+    if (kAcc && !visible) {
+        p.dL_dmeans2D[3 * idx + 0] = 0.f;
+        p.dL_dmeans2D[3 * idx + 1] = 0.f;
+        p.dL_dmeans2D[3 * idx + 2] = 0.f;
+        return;
+    }
     const float* g = p.grad_arena + (size_t)idx * p.grad_stride;
 
     float dT[9], dm2x = 0.f, dm2y = 0.f, dopa = 0.f, dn[3] = {0.f, 0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f};
@@ -136,21 +156,21 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     }
 
     // pass-through outputs
-    p.dL_dopacity[idx] = dopa;
+    put<kAcc>(p.dL_dopacity + idx, dopa);
     if (p.dL_dcolors != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) p.dL_dcolors[3 * idx + c] = dcol[c];
+        for (int c = 0; c < 3; ++c) put<kAcc>(p.dL_dcolors + 3 * idx + c, dcol[c]);
     }
     if ((p.S & 3) == 0) {
         // arena features start at float 18: not 16-byte aligned, so gather scalars, store vectors
         for (int c = 0; c < p.S; c += 4) {
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (visible) v = make_float4(g[kGradFeature + c], g[kGradFeature + c + 1], g[kGradFeature + c + 2], g[kGradFeature + c + 3]);
-            reinterpret_cast<float4*>(p.dL_dfeatures + (size_t)idx * p.S)[c >> 2] = v;
+            put<kAcc>(reinterpret_cast<float4*>(p.dL_dfeatures + (size_t)idx * p.S) + (c >> 2), v);
         }
     } else {
         for (int c = 0; c < p.S; ++c)
-            p.dL_dfeatures[(size_t)idx * p.S + c] = visible ? g[kGradFeature + c] : 0.f;
+            put<kAcc>(p.dL_dfeatures + (size_t)idx * p.S + c, visible ? g[kGradFeature + c] : 0.f);
     }
 
     float dmean3[3] = {0.f, 0.f, 0.f}, dscale[2] = {0.f, 0.f}, drot[4] = {0.f, 0.f, 0.f, 0.f};
@@ -275,7 +295,7 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
         const bool precomp = (p.scales == nullptr);
 #pragma unroll
         for (int i = 0; i < 9; ++i)
-            p.dL_dtransMat[9 * idx + i] = visible ? (precomp ? dT[i] : g[kGradT + i]) : 0.f;
+            put<kAcc>(p.dL_dtransMat + 9 * idx + i, visible ? (precomp ? dT[i] : g[kGradT + i]) : 0.f);
     }
 
     // SH coefficients and their contribution to the position gradient
@@ -302,7 +322,13 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
                 float4* dst = reinterpret_cast<float4*>(dsh);
 #pragma unroll
                 for (int q = 0; q < 12; ++q)
-                    dst[q] = make_float4(dsh_l[4 * q], dsh_l[4 * q + 1], dsh_l[4 * q + 2], dsh_l[4 * q + 3]);
+                    put<kAcc>(dst + q, make_float4(dsh_l[4 * q], dsh_l[4 * q + 1], dsh_l[4 * q + 2], dsh_l[4 * q + 3]));
+            } else if (kAcc) {
+                // generic coefficient count (M <= 16, checked by the caller): stage the row, then add it
+                float dsh_l[48];
+                for (int k = 0; k < 48; ++k) dsh_l[k] = 0.f;
+                dpos = sh_backward<false>(p.D, p.M, p.shs + (size_t)idx * p.M * 3, pos, cam, gc, dsh_l);
+                for (int k = 0; k < p.M * 3; ++k) dsh[k] += dsh_l[k];
             } else {
                 dpos = sh_backward<true>(p.D, p.M, p.shs + (size_t)idx * p.M * 3, pos, cam, gc, dsh);
             }
@@ -319,20 +345,23 @@ __global__ void __launch_bounds__(256) preprocess_bwd_kernel(const PreprocessBwd
     }
 
 #pragma unroll
-    for (int k = 0; k < 3; ++k) p.dL_dmeans3D[3 * idx + k] = dmean3[k];
+    for (int k = 0; k < 3; ++k) put<kAcc>(p.dL_dmeans3D + 3 * idx + k, dmean3[k]);
     p.dL_dmeans2D[3 * idx + 0] = proxy_x;
     p.dL_dmeans2D[3 * idx + 1] = proxy_y;
     p.dL_dmeans2D[3 * idx + 2] = 0.f;
     if (p.dL_dscales != nullptr)
-        reinterpret_cast<float2*>(p.dL_dscales)[idx] = make_float2(dscale[0], dscale[1]);
+        put<kAcc>(reinterpret_cast<float2*>(p.dL_dscales) + idx, make_float2(dscale[0], dscale[1]));
     if (p.dL_drotations != nullptr)
-        reinterpret_cast<float4*>(p.dL_drotations)[idx] = make_float4(drot[0], drot[1], drot[2], drot[3]);
+        put<kAcc>(reinterpret_cast<float4*>(p.dL_drotations) + idx, make_float4(drot[0], drot[1], drot[2], drot[3]));
 }
 
 }  // namespace
 
 void launch_preprocess_bwd(const PreprocessBwdParams& p, cudaStream_t stream) {
-    preprocess_bwd_kernel<<<(p.P + 255) / 256, 256, 0, stream>>>(p);
+    if (p.accumulate)
+        preprocess_bwd_kernel<true><<<(p.P + 255) / 256, 256, 0, stream>>>(p);
+    else
+        preprocess_bwd_kernel<false><<<(p.P + 255) / 256, 256, 0, stream>>>(p);
 }
 
 }  // namespace mrgs

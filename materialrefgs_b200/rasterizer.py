@@ -156,10 +156,14 @@ def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales,
                            scale_modifier, transMat_precomp, viewmatrix, projmatrix, tanfovx,
                            tanfovy, dL_dout_color, dL_dout_feature, dL_dout_others, sh, sh_degree,
                            campos, geom, num_rendered, binning, image, contrib, debug, need_colors=True,
-                           need_transmat=True):
+                           need_transmat=True, accumulate_into=None):
     """Equivalent of _C.rasterize_gaussians_backward (rast/rasterize_points.cu:146-252): returns
     (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
-    dL_dscales, dL_drotations)."""
+    dL_dscales, dL_drotations).
+
+    accumulate_into: optional {"means3D","shs","features","opacities","scales","rotations"} -> fp32 CUDA
+    buffers; the parameter gradients are then ADDED to those buffers by the kernel itself (and the same
+    tensors are returned) instead of being written to fresh tensors (MrgsBackwardArgs.accumulate)."""
     lib = _lib.load()
     dev = means3D.device
     P = means3D.shape[0]
@@ -174,6 +178,23 @@ def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales,
     (dL_dmeans2D, dL_dcolors, dL_dfeatures, dL_dopacity, dL_dmeans3D, dL_dtransMat, dL_dsh,
      dL_dscales, dL_drotations) = (torch.empty(s, **f32) for s in out_shapes)
     has_sr = scales.numel() != 0
+    if accumulate_into is not None:
+        if not has_sr or M == 0:
+            raise RuntimeError("accumulate_into needs the scales/rotations + SH input combination")
+
+        def _sink(name, shape):
+            t = accumulate_into[name]
+            n = 1
+            for d in shape:
+                n *= d
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and t.numel() == n):
+                raise RuntimeError(f"accumulate_into[{name!r}] must be a contiguous float32 CUDA tensor of {n} elements")
+            return t
+        dL_dmeans3D, dL_dsh = _sink("means3D", (P, 3)), _sink("shs", (P, M, 3))
+        dL_dopacity, dL_dscales, dL_drotations = _sink("opacities", (P, 1)), _sink("scales", (P, 2)), _sink("rotations", (P, 4))
+        if S:
+            dL_dfeatures = _sink("features", (P, S))
+        need_colors = need_transmat = False
     if not has_sr:  # never written for precomputed transforms; the reference returns zeros
         dL_dscales.zero_(); dL_drotations.zero_()
     if M == 0:
@@ -207,6 +228,7 @@ def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales,
     a.dL_dscales = _ptr(dL_dscales) if has_sr else None
     a.dL_drotations = _ptr(dL_drotations) if has_sr else None
     a.grad_arena, a.grad_arena_bytes = arena.data_ptr(), arena.numel()
+    a.accumulate = int(accumulate_into is not None)
 
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -233,16 +255,23 @@ def _cpu_deep_copy_tuple(input_tuple):
 
 
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
-                        cov3Ds_precomp, raster_settings):
+                        cov3Ds_precomp, raster_settings, grad_sink=None):
+    if grad_sink is not None:
+        for name, t in (("means3D", means3D), ("shs", sh), ("features", features), ("opacities", opacities),
+                        ("scales", scales), ("rotations", rotations)):
+            if t.requires_grad and not t.is_leaf:
+                raise RuntimeError(f"grad_sink: {name} is not a leaf tensor; fused gradient accumulation bypasses "
+                                   "autograd and is only valid for parameters")
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, features, opacities,
-                                     scales, rotations, cov3Ds_precomp, raster_settings)
+                                     scales, rotations, cov3Ds_precomp, raster_settings, grad_sink)
 
 
 class _RasterizeGaussians(torch.autograd.Function):
     @staticmethod
     def forward(ctx, means3D, means2D, sh, colors_precomp, features, opacities, scales, rotations,
-                cov3Ds_precomp, raster_settings):
+                cov3Ds_precomp, raster_settings, grad_sink=None):
         rs = raster_settings
+        ctx.grad_sink = grad_sink
         args = (rs.bg, means3D, colors_precomp, features, opacities, scales, rotations, rs.scale_modifier,
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, rs.image_height,
                 rs.image_width, sh, rs.sh_degree, rs.campos, rs.prefiltered, rs.debug)
@@ -273,7 +302,8 @@ class _RasterizeGaussians(torch.autograd.Function):
                 cov3Ds_precomp, rs.viewmatrix, rs.projmatrix, rs.tanfovx, rs.tanfovy, grad_out_color,
                 grad_out_feature, grad_depth, sh, rs.sh_degree, rs.campos, geom, ctx.num_rendered,
                 binning, image, contrib, rs.debug)
-        want = dict(need_colors=ctx.needs_input_grad[3], need_transmat=ctx.needs_input_grad[8])
+        want = dict(need_colors=ctx.needs_input_grad[3], need_transmat=ctx.needs_input_grad[8],
+                    accumulate_into=ctx.grad_sink)
         if rs.debug:  # same failure artefact as the reference (rast/diff_surfel_rasterization/__init__.py:141-148)
             cpu_args = _cpu_deep_copy_tuple(args)
             try:
@@ -290,15 +320,22 @@ class _RasterizeGaussians(torch.autograd.Function):
             grad_colors_precomp = None
         if not ctx.needs_input_grad[8]:
             grad_cov3Ds_precomp = None
+        if ctx.grad_sink is not None:
+            # the kernel has already added these into the sink: nothing for autograd to accumulate
+            return (None, grad_means2D, None, None, None, None, None, None, None, None, None)
         # one gradient per forward input (the reference returns a surplus trailing None)
         return (grad_means3D, grad_means2D, grad_sh, grad_colors_precomp, grad_features,
-                grad_opacities, grad_scales, grad_rotations, grad_cov3Ds_precomp, None)
+                grad_opacities, grad_scales, grad_rotations, grad_cov3Ds_precomp, None, None)
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings):
+    def __init__(self, raster_settings, grad_sink=None):
+        """grad_sink (extension, optional): {"means3D","shs","features","opacities","scales","rotations"} ->
+        buffers the backward ADDS the parameter gradients into (e.g. parallel.GradArena.views) instead of
+        returning them to autograd; only valid when those inputs are leaf parameters."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.grad_sink = grad_sink
 
     def markVisible(self, positions):
         with torch.no_grad():
@@ -327,4 +364,4 @@ class GaussianRasterizer(nn.Module):
         if cov3D_precomp is None:
             cov3D_precomp = empty()
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales,
-                                   rotations, cov3D_precomp, rs)
+                                   rotations, cov3D_precomp, rs, self.grad_sink)

@@ -55,3 +55,43 @@ def test_rasterizer_grads_accumulate_in_place_into_bound_arena():
     for k in names:   # the backward's atomics make two runs equal only up to summation order
         ref = free[k].grad.reshape(P, -1)
         assert float((arena.views[k] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-12, k
+
+
+def test_grad_sink_fused_accumulation_matches_autograd():
+    """GaussianRasterizer(..., grad_sink=arena.views): the per-surfel backward ADDS every view's parameter
+    gradients into the arena itself (MrgsBackwardArgs.accumulate); result == autograd accumulation, the leaves'
+    bound .grad sees it, means2D still gets its per-view gradient, non-leaf inputs are refused."""
+    from materialrefgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    dev = torch.device("cuda:0")
+    P, S, W, H = 6000, 8, 176, 128
+    cloud = synthetic.make_cloud(P, S=S, seed=4).to(dev)
+    names = ("means3D", "scales", "rotations", "opacities", "shs", "features")
+    sunk = {k: getattr(cloud, k).clone().requires_grad_(True) for k in names}
+    free = {k: getattr(cloud, k).clone().requires_grad_(True) for k in names}
+    arena = parallel.GradArena.create(P, dev)
+    arena.bind(sunk)
+    arena.zero_()
+    bg = torch.zeros(3, device=dev)
+    m2_grads = {}
+    for v in (0, 3, 6):
+        cam = synthetic.orbit_camera(v, 8, W, H).to(dev)
+        rs = GaussianRasterizationSettings(H, W, cam.tanfovx, cam.tanfovy, bg, 1.0, cam.world_view_transform,
+                                           cam.full_proj_transform, 3, cam.camera_center, False, False)
+        for tag, L, sink in (("sunk", sunk, arena.views), ("free", free, None)):
+            m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+            _, color, feat, radii, allmap = GaussianRasterizer(rs, grad_sink=sink)(
+                means3D=L["means3D"], means2D=m2, opacities=L["opacities"], shs=L["shs"], features=L["features"],
+                scales=L["scales"], rotations=L["rotations"])
+            (color.sum() + feat.square().sum() + allmap[1].sum() + allmap[0].sum()).backward()
+            m2_grads[tag] = m2.grad
+        assert float((m2_grads["sunk"] - m2_grads["free"]).abs().max()) <= 1e-5 * float(m2_grads["free"].abs().max())
+    assert arena.bound(sunk)
+    for k in names:
+        ref = free[k].grad.reshape(P, -1)
+        assert float((arena.views[k] - ref).abs().max()) <= 1e-5 * float(ref.abs().max()) + 1e-12, k
+        assert sunk[k].grad.data_ptr() == arena.views[k].data_ptr()
+    # a computed (non-leaf) input cannot bypass autograd
+    with pytest.raises(RuntimeError):
+        GaussianRasterizer(rs, grad_sink=arena.views)(
+            means3D=sunk["means3D"], means2D=None, opacities=torch.sigmoid(sunk["opacities"]), shs=sunk["shs"],
+            features=sunk["features"], scales=sunk["scales"], rotations=sunk["rotations"])
