@@ -594,23 +594,40 @@ emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t*
     }
 }
 
+// Tile boundaries in the sorted 16-bit tile ids. Every thread owns 8 consecutive keys (one 16-byte load) plus the
+// key before them, so the 2-byte keys are read with full-width coalesced accesses.
 __global__ void __launch_bounds__(256)
 identify_tile_ranges_kernel(int R, const uint32_t* __restrict__ n_dev, const uint16_t* __restrict__ keys,
                             uint2* __restrict__ ranges) {
     if (n_dev != nullptr) R = min(R, (int)*n_dev);
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= R) return;
-    const uint32_t tile = keys[idx];
-    if (idx == 0) {
-        ranges[tile].x = 0;
+    const int first = (blockIdx.x * blockDim.x + threadIdx.x) * 8;
+    if (first >= R) return;
+    uint32_t k[8];
+    if (first + 8 <= R) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(keys + first);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k[e] = (w[e >> 1] >> ((e & 1) * 16)) & 0xffffu;
     } else {
-        const uint32_t prev = keys[idx - 1];
-        if (tile != prev) {
-            ranges[prev].y = idx;
-            ranges[tile].x = idx;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) k[e] = (first + e < R) ? (uint32_t)keys[first + e] : 0u;
+    }
+    uint32_t prev = (first == 0) ? 0u : (uint32_t)keys[first - 1];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        const int idx = first + e;
+        if (idx < R) {
+            const uint32_t tile = k[e];
+            if (idx == 0) {
+                ranges[tile].x = 0;
+            } else if (tile != prev) {
+                ranges[prev].y = idx;
+                ranges[tile].x = idx;
+            }
+            if (idx == R - 1) ranges[tile].y = R;
+            prev = tile;
         }
     }
-    if (idx == R - 1) ranges[tile].y = R;
 }
 
 }  // namespace
@@ -654,7 +671,7 @@ int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* va
 }
 
 void launch_identify_tile_ranges(int R, const uint32_t* R_dev, const uint16_t* keys, uint2* ranges, cudaStream_t stream) {
-    identify_tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, R_dev, keys, ranges);
+    identify_tile_ranges_kernel<<<(R + 2047) / 2048, 256, 0, stream>>>(R, R_dev, keys, ranges);
 }
 
 bool radix_lookback_enabled() { return use_lookback(); }
