@@ -38,11 +38,15 @@ static int32_t* pinned_slot() {
 }
 
 static cudaEvent_t r_ready_event() {
-    static thread_local cudaEvent_t ev = nullptr;
-    if (ev == nullptr) {
-        if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    // one event per (thread, device): an event can only be recorded on a stream of the device it was created on
+    constexpr int kMaxDevices = 64;
+    static thread_local cudaEvent_t ev[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return nullptr;
+    if (ev[dev] == nullptr) {
+        if (cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming) != cudaSuccess) ev[dev] = nullptr;
     }
-    return ev;
+    return ev[dev];
 }
 
 // ---- optional per-stage timing (CUDA events on the launching stream) + own-kernel launch count
