@@ -373,6 +373,48 @@ MRGS_API int mrgs_photometric_forward(const float* img, const float* gt, int32_t
 MRGS_API int mrgs_photometric_backward(const float* img, const float* gt, const float* maps, int32_t channels,
                                        int32_t height, int32_t width, const float* upstream, float* dimg, void* stream);
 
+/* Geometric regularisers of calculate_loss (utils/loss_utils.py:160-197) on one view's maps, ONE
+ * forward and ONE backward kernel. `terms` selects what is evaluated (members of the other terms may be NULL):
+ *   MRGS_GEOM_NORMAL         out4[0] = mean_{HW}( image_weight * sum_c |surf_normal_c - rend_normal_c| )   (:169)
+ *                                      or, with image_weight == NULL, mean_{HW}( 1 - sum_c rend_normal_c surf_normal_c ) (:171-172)
+ *   MRGS_GEOM_DIST           out4[1] = mean_{HW}( rend_dist )                                               (:177)
+ *   MRGS_GEOM_NORMAL_SMOOTH  out4[2] = first_order_edge_aware_loss(rend_normal, gt_image)                   (:121-122, :183)
+ *   MRGS_GEOM_DEPTH_SMOOTH   out4[3] = first_order_edge_aware_loss(surf_depth,  gt_image)                   (:191)
+ * first_order_edge_aware_loss(data, img) = mean_{3HW}( sum_{d in x,y} |grad_d data| * exp(-|grad_d img|) ) with
+ * kornia 0.7.3's spatial_gradient (normalised 3x3 Sobel, replicate padding). Terms not selected give 0.
+ * forward : `coef` ([8][H][W] scratch, may be NULL when no gradient is wanted) keeps sign(grad data) * exp(-|grad img|);
+ *           `partials` is scratch of mrgs_geometry_loss_partials_bytes(); out4 is device [4].
+ * backward: upstream = device [4] = dL/d out4; every non-NULL dL_d* map is written in full (zeros where a term is off).
+ *           gt_image and image_weight have no gradient (the reference detaches them). Deterministic. */
+#define MRGS_GEOM_NORMAL 1u
+#define MRGS_GEOM_DIST 2u
+#define MRGS_GEOM_NORMAL_SMOOTH 4u
+#define MRGS_GEOM_DEPTH_SMOOTH 8u
+typedef struct MrgsGeometryLossArgs {
+    int32_t height, width;
+    uint32_t terms;
+    const float* rend_normal;   /* [3,H,W] */
+    const float* surf_normal;   /* [3,H,W] */
+    const float* rend_dist;     /* [1,H,W] */
+    const float* surf_depth;    /* [1,H,W] */
+    const float* gt_image;      /* [3,H,W] */
+    const float* image_weight;  /* [H,W] or NULL */
+    float* coef;                /* [8,H,W] scratch, forward writes / backward reads */
+    float* partials;            /* scratch */
+    float* out4;                /* forward output  */
+    const float* upstream;      /* backward input  */
+    float *dL_drend_normal, *dL_dsurf_normal, *dL_drend_dist, *dL_dsurf_depth;   /* backward outputs, each may be NULL */
+} MrgsGeometryLossArgs;
+MRGS_API size_t mrgs_geometry_loss_partials_bytes(int32_t height, int32_t width);
+MRGS_API int mrgs_geometry_loss_forward(const MrgsGeometryLossArgs* args, void* stream);
+MRGS_API int mrgs_geometry_loss_backward(const MrgsGeometryLossArgs* args, void* stream);
+
+/* get_img_grad_weight (utils/loss_utils.py:127-139): per interior pixel max( mean_c |right - left|, mean_c |top - bottom| ),
+ * normalised by the interior's min and max, border padded with 1. img [C,H,W] -> out [H,W]; H, W >= 3;
+ * scratch8 = 8 bytes of device memory. */
+MRGS_API int mrgs_img_grad_weight(const float* img, int32_t channels, int32_t height, int32_t width, float* out,
+                                  void* scratch8, void* stream);
+
 /* Densification statistics of one rendered view, one fused pass over the P surfels
  * (GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061 and the max_radii2D update
  * train_refnerf.py:1416-1418). For every surfel with radii > 0:

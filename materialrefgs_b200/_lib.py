@@ -102,6 +102,17 @@ class SurfelFeatureArgs(C.Structure):
         "dL_drefl_strength", "dL_droughness", "dL_dori_color", "dL_dindirect_dc", "dL_dindirect_rest")]
 
 
+
+GEOM_NORMAL, GEOM_DIST, GEOM_NORMAL_SMOOTH, GEOM_DEPTH_SMOOTH = 1, 2, 4, 8
+
+
+class GeometryLossArgs(C.Structure):
+    """MrgsGeometryLossArgs (include/mrgs.h)."""
+    _fields_ = [("height", C.c_int32), ("width", C.c_int32), ("terms", C.c_uint32)] + [(n, _fp) for n in (
+        "rend_normal", "surf_normal", "rend_dist", "surf_depth", "gt_image", "image_weight", "coef", "partials", "out4",
+        "upstream", "dL_drend_normal", "dL_dsurf_normal", "dL_drend_dist", "dL_dsurf_depth")]
+
+
 SYMBOLS = {
     "mrgs_abi_version": (C.c_int, []),
     "mrgs_last_error": (C.c_char_p, []),
@@ -140,6 +151,10 @@ SYMBOLS = {
     "mrgs_photometric_partials_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "mrgs_photometric_forward": (C.c_int, [_fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, _fp, C.c_void_p]),
     "mrgs_photometric_backward": (C.c_int, [_fp, _fp, _fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, C.c_void_p]),
+    "mrgs_geometry_loss_partials_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "mrgs_geometry_loss_forward": (C.c_int, [C.POINTER(GeometryLossArgs), C.c_void_p]),
+    "mrgs_geometry_loss_backward": (C.c_int, [C.POINTER(GeometryLossArgs), C.c_void_p]),
+    "mrgs_img_grad_weight": (C.c_int, [_fp, C.c_int32, C.c_int32, C.c_int32, _fp, _fp, C.c_void_p]),
     "mrgs_densify_stats": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
 }
 

@@ -33,6 +33,7 @@ SOURCES = [
     "cubemap.cu",
     "features.cu",
     "losses.cu",
+    "geomloss.cu",
 ]
 
 NVCC_FLAGS = [

@@ -278,6 +278,57 @@ int mrgs_photometric_backward(const float* img, const float* gt, const float* ma
     return MRGS_OK;
 }
 
+size_t mrgs_geometry_loss_partials_bytes(int32_t H, int32_t W) {
+    if (H <= 0 || W <= 0) return 0;
+    return geometry_loss_partials_count(H, W) * sizeof(float4);
+}
+
+static bool geometry_loss_args_ok(const MrgsGeometryLossArgs* a, bool backward) {
+    if (!a || a->height <= 0 || a->width <= 0) return false;
+    const unsigned t = a->terms;
+    if (t & ~(MRGS_GEOM_NORMAL | MRGS_GEOM_DIST | MRGS_GEOM_NORMAL_SMOOTH | MRGS_GEOM_DEPTH_SMOOTH)) return false;
+    if ((t & MRGS_GEOM_NORMAL) && (!a->rend_normal || !a->surf_normal)) return false;
+    if ((t & MRGS_GEOM_DIST) && !a->rend_dist) return false;
+    if ((t & MRGS_GEOM_NORMAL_SMOOTH) && (!a->rend_normal || !a->gt_image)) return false;
+    if ((t & MRGS_GEOM_DEPTH_SMOOTH) && (!a->surf_depth || !a->gt_image)) return false;
+    if (!backward) return a->partials && a->out4;
+    if ((t & (MRGS_GEOM_NORMAL_SMOOTH | MRGS_GEOM_DEPTH_SMOOTH)) && !a->coef) return false;
+    return a->upstream != nullptr;
+}
+
+int mrgs_geometry_loss_forward(const MrgsGeometryLossArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!geometry_loss_args_ok(a, false)) {
+        set_error("mrgs_geometry_loss_forward: bad arguments (a map of a selected term is NULL, or H/W <= 0)");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    launch_geometry_loss(a, false, stream);
+    MRGS_LAUNCH_OK("geometry_loss_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_geometry_loss_backward(const MrgsGeometryLossArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!geometry_loss_args_ok(a, true)) {
+        set_error("mrgs_geometry_loss_backward: bad arguments (a map of a selected term, coef or upstream is NULL)");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    launch_geometry_loss(a, true, stream);
+    MRGS_LAUNCH_OK("geometry_loss_bwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_img_grad_weight(const float* img, int32_t C, int32_t H, int32_t W, float* out, void* scratch8, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!img || !out || !scratch8 || C <= 0 || H < 3 || W < 3) {
+        set_error("mrgs_img_grad_weight: bad arguments (C=%d H=%d W=%d; H, W >= 3)", C, H, W);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    launch_img_grad_weight(img, C, H, W, out, scratch8, stream);
+    MRGS_LAUNCH_OK("img_grad_weight", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_densify_stats(int32_t P, const float* dL_dmeans2D, const int32_t* radii, float* stats,
                        int32_t* max_radii, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;

@@ -125,6 +125,9 @@ int launch_photometric_fwd(const float* img, const float* gt, int C, int H, int 
                            float* out2, cudaStream_t stream);
 int launch_photometric_bwd(const float* img, const float* gt, const float* maps, int C, int H, int W,
                            const float* upstream, float* dimg, cudaStream_t stream);
+size_t geometry_loss_partials_count(int H, int W);
+int launch_geometry_loss(const MrgsGeometryLossArgs* a, bool backward, cudaStream_t stream);
+int launch_img_grad_weight(const float* img, int C, int H, int W, float* out, void* scratch8, cudaStream_t stream);
 int launch_surfel_features(const MrgsSurfelFeatureArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream);
