@@ -114,3 +114,53 @@ def test_bound_arena_receives_autograd_accumulation_in_place():
     assert arena.grads.numel() == P * 66 and arena.flat.numel() == P * 68
     arena.zero_()
     assert float(leaves["shs"].grad.abs().max()) == 0.0
+
+
+# ---- densification after a view-sharded step: every rank must arrive at the same cloud without a broadcast ----
+def _densify_worker(rank, world, port, q):
+    from materialrefgs_b200 import surfel_model as sm
+    if world > 1:
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(7)
+        fields = {n: 0.3 * torch.randn((P, *f.shape), generator=g) for n, f in sm.FIELDS.items()}
+        fields["scaling"] = torch.log(0.02 * torch.exp(0.8 * torch.randn((P, 2), generator=g)))
+        store = sm.SurfelStore(fields)
+        arena = parallel.GradArena.create(P, "cpu")
+
+        def render(i):
+            v = fake_view(i)
+            v["viewspace_grad"] = 4e-4 * v["viewspace_grad"]
+            v["viewspace_grad"][:, 2] = 0.0          # the rasterizer's screen-space gradient has no z part
+            return v
+        parallel.train_step_view_sharded(render, NV, arena)
+        store.load_reduced_stats(arena.stats, arena.max_radii)
+        gen = torch.Generator().manual_seed(1234)    # same seed on every rank
+        store.densify_and_prune(0.0002, 0.05, 2.5, 20, generator=gen)
+        q.put((rank, store.num_points, store.checksum().tolist(), store["xyz"].detach().clone()))
+    finally:
+        if world > 1:
+            dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_ranks_densify_to_the_same_cloud_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_densify_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=100) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    single = ctx.Queue()
+    _densify_worker(0, 1, 0, single)
+    ref = single.get(timeout=10)
+    assert res[0][1] == res[1][1] == ref[1] != P
+    assert res[0][2] == res[1][2]
+    assert torch.equal(res[0][3], res[1][3])
+    assert torch.allclose(res[0][3], ref[3], atol=1e-6)      # sharded sum order differs from the serial one by rounding only

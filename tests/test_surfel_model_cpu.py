@@ -1,0 +1,128 @@
+"""CPU: materialrefgs_b200/surfel_model.py — the .ply format and the densification bookkeeping against
+vectors produced by the reference's own GaussianModel methods (tests/golden/make_golden_densify.py)."""
+import glob
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from materialrefgs_b200 import surfel_model as sm
+
+ROOT = Path(__file__).resolve().parent.parent
+GOLDEN = sorted(glob.glob(str(ROOT / "tests" / "golden" / "densify_*.npz")))
+
+
+def random_fields(P, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return {n: torch.randn((P, *f.shape), generator=g) for n, f in sm.FIELDS.items()}
+
+
+def test_attribute_order_is_the_reference_one():
+    names = sm.construct_list_of_attributes()
+    # scene/gaussian_model.py:462-487 with f_dc 1x3, f_rest 15x3, ind_dc 1x3, ind_rest 15x3, ind_asg 32x5
+    assert names[:9] == ["x", "y", "z", "nx", "ny", "nz", "nx2", "ny2", "nz2"]
+    assert names[9:12] == ["f_dc_0", "f_dc_1", "f_dc_2"] and names[12] == "f_rest_0" and names[56] == "f_rest_44"
+    assert names[57:60] == ["ind_dc_0", "ind_dc_1", "ind_dc_2"] and names[60] == "ind_rest_0" and names[104] == "ind_rest_44"
+    assert names[105] == "ind_asg_0" and names[264] == "ind_asg_159"
+    assert names[265:269] == ["opacity", "refl_strength", "metalness", "roughness"]
+    assert names[269:275] == ["ori_color_0", "ori_color_1", "ori_color_2", "diffuse_color_0", "diffuse_color_1", "diffuse_color_2"]
+    assert names[275:] == ["scale_0", "scale_1", "rot_0", "rot_1", "rot_2", "rot_3"]
+    assert len(names) == 281
+
+
+def test_ply_round_trip_and_header(tmp_path):
+    f = random_fields(37, seed=3)
+    path = tmp_path / "point_cloud" / "iteration_7" / "point_cloud.ply"
+    sm.save_ply(path, f)
+    raw = path.read_bytes()
+    head, _, body = raw.partition(b"end_header\n")
+    lines = head.decode().splitlines()
+    assert lines[:3] == ["ply", "format binary_little_endian 1.0", "element vertex 37"]
+    assert lines[3:] == [f"property float {n}" for n in sm.construct_list_of_attributes()]
+    assert len(body) == 37 * 281 * 4
+    table = np.frombuffer(body, dtype="<f4").reshape(37, 281)
+    # channel-major SH columns: f_rest_k = features_rest[:, k % 15, k // 15]  (transpose(1, 2).flatten, :495)
+    assert np.array_equal(table[:, 12 + 17], f["features_rest"][:, 2, 1].numpy())
+    assert np.array_equal(table[:, 105 + 33], f["indirect_asg"][:, 1, 1].numpy())   # [P,32,5] -> [P,5,32]
+    back = sm.load_ply(path)
+    for n in sm.FIELDS:
+        assert back[n].shape == tuple(f[n].shape) and np.array_equal(back[n], f[n].numpy()), n
+    # attribute lookup is by name: a file with shuffled columns loads the same
+    order = np.random.default_rng(0).permutation(281)
+    names = sm.construct_list_of_attributes()
+    shuffled = tmp_path / "shuffled.ply"
+    hdr = ["ply", "format binary_little_endian 1.0", "comment written by a test", "element vertex 37"]
+    hdr += [f"property float {names[i]}" for i in order] + ["end_header"]
+    shuffled.write_bytes(("\n".join(hdr) + "\n").encode() + np.ascontiguousarray(table[:, order]).tobytes())
+    back2 = sm.load_ply(shuffled)
+    for n in sm.FIELDS:
+        assert np.array_equal(back2[n], f[n].numpy()), n
+    with pytest.raises(ValueError):
+        sm.load_ply(path, max_sh_degree=2)
+    store = sm.SurfelStore.from_ply(path)
+    assert store.num_points == 37 and torch.equal(store["rotation"].detach(), f["rotation"])
+
+
+def store_from_golden(z, prefix="before_"):
+    fields = {n: torch.from_numpy(z[prefix + "p_" + f.group]) for n, f in sm.FIELDS.items()}
+    st = sm.SurfelStore(fields, percent_dense=float(z["percent_dense"]))
+    for n, f in sm.FIELDS.items():
+        if prefix + "m_" + f.group in z.files:
+            st.optimizer.state[st[n]] = {"step": torch.tensor(2.0), "exp_avg": torch.from_numpy(z[prefix + "m_" + f.group]).clone(),
+                                        "exp_avg_sq": torch.from_numpy(z[prefix + "v_" + f.group]).clone()}
+    return st
+
+
+def test_golden_files_present():
+    assert len(GOLDEN) >= 2
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: Path(p).stem)
+def test_densification_matches_reference_methods(path):
+    z = np.load(path)
+    st = store_from_golden(z)
+    for g, filt, radii in zip(z["view_grads"], z["view_filters"], z["view_radii"]):
+        st.add_densification_stats(torch.from_numpy(g), torch.from_numpy(filt), torch.from_numpy(radii))
+    assert np.array_equal(st.xyz_gradient_accum.numpy(), z["stats_xyz_gradient_accum"])
+    assert np.array_equal(st.denom.numpy(), z["stats_denom"])
+    assert np.array_equal(st.max_radii2D.numpy(), z["stats_max_radii2D"])
+    torch.manual_seed(int(z["seed"]) + 300)
+    mss = int(z["max_screen_size"])
+    st.densify_and_prune(float(z["max_grad"]), float(z["min_opacity"]), float(z["extent"]), None if mss < 0 else mss)
+    assert st.num_points == z["after_p_xyz"].shape[0] != int(z["P"])
+    for n, f in sm.FIELDS.items():
+        assert np.array_equal(st[n].detach().numpy(), z["after_p_" + f.group]), n
+        state = st.optimizer.state.get(st[n], None)
+        if "after_m_" + f.group in z.files:
+            assert np.array_equal(state["exp_avg"].numpy(), z["after_m_" + f.group]), n
+            assert np.array_equal(state["exp_avg_sq"].numpy(), z["after_v_" + f.group]), n
+        else:
+            assert state is None or "exp_avg" not in state
+    for k in ("xyz_gradient_accum", "denom", "max_radii2D"):
+        assert np.array_equal(getattr(st, k).numpy(), z["after_" + k]), k
+    st.reset_opacity0()
+    assert np.array_equal(st["opacity"].detach().numpy(), z["reset_p_opacity"])
+    assert np.array_equal(st.optimizer.state[st["opacity"]]["exp_avg"].numpy(), z["reset_m_opacity"])
+    # the optimizer still steps on the rebuilt parameters
+    for p in st.params.values():
+        p.grad = torch.ones_like(p)
+    st.optimizer.step()
+
+
+def test_reduced_stats_equal_per_view_accumulation():
+    P = 50
+    g = torch.Generator().manual_seed(1)
+    a, b = sm.SurfelStore(random_fields(P)), sm.SurfelStore(random_fields(P))
+    stats, mx = torch.zeros(P, 2), torch.zeros(P, dtype=torch.int32)
+    for _ in range(3):
+        grad = torch.randn(P, 3, generator=g)
+        radii = (torch.randint(0, 30, (P,), generator=g) * (torch.rand(P, generator=g) > 0.4)).int()
+        filt = radii > 0
+        a.add_densification_stats(grad, filt, radii)
+        stats[filt, 0] += grad[filt].norm(dim=-1)
+        stats[filt, 1] += 1
+        mx = torch.maximum(mx, radii)
+    b.load_reduced_stats(stats, mx)
+    assert torch.allclose(a.xyz_gradient_accum, b.xyz_gradient_accum) and torch.equal(a.denom, b.denom)
+    assert torch.equal(a.max_radii2D, b.max_radii2D)
