@@ -287,9 +287,17 @@ MRGS_API int mrgs_shade_backward(const MrgsShadeArgs* args, void* stream);
 
 /* EnvLight.__call__ (scene/light.py:98-129) for arbitrary directions: out[i] = sigmoid(cube fetch of
  * dirs[i] at mip level get_mip(roughness[i])) (mode "specular"), or a plain bilinear fetch of
- * levels[0] when roughness == NULL (modes "diffuse"/"pure_env"). n directions, out [n,3]. */
+ * levels[0] when roughness == NULL (modes "diffuse"/"pure_env"; the chain may then hold one level).
+ * n directions, out [n,3]. */
 MRGS_API int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs,
                                  const float* roughness, float* out, void* stream);
+/* Backward of mrgs_envlight_query (nvdiffrast's dr.texture backward + the sigmoid, scene/light.py:108-129): with
+ * dL_dout [n,3], texel gradients are ADDED into chain->dL_dlevels[l] (float4 per texel, rgb + pad, like
+ * mrgs_shade_backward; a NULL level is skipped), dL_ddirs [n,3] and dL_droughness [n] are written when non-NULL.
+ * With roughness == NULL the chain may hold a single level (modes "diffuse" / "pure_env"). */
+MRGS_API int mrgs_envlight_query_backward(const MrgsShadeArgs* chain, int64_t n, const float* dirs,
+                                          const float* roughness, const float* dL_dout, float* dL_ddirs,
+                                          float* dL_droughness, void* stream);
 
 /* ---- pseudo surface depth + depth_to_normal ------------------------------------------------------
  * compute_2dgs_normal_and_regularizations (gaussian_renderer/__init__.py:50-78) + depth_to_normal

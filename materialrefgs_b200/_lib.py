@@ -132,6 +132,7 @@ SYMBOLS = {
     "mrgs_shade_forward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_shade_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_envlight_query": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_envlight_query_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "mrgs_depth_normal_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                             _fp, _fp, _fp, C.c_void_p]),
     "mrgs_depth_normal_backward": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),

@@ -623,6 +623,23 @@ int mrgs_envlight_query(const MrgsShadeArgs* chain, int64_t n, const float* dirs
     return MRGS_OK;
 }
 
+int mrgs_envlight_query_backward(const MrgsShadeArgs* chain, int64_t n, const float* dirs, const float* roughness,
+                                 const float* dL_dout, float* dL_ddirs, float* dL_droughness, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n > 0 && (dirs == nullptr || dL_dout == nullptr)) {
+        set_error("mrgs_envlight_query_backward: null dirs/dL_dout");
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_BWD, stream, 1);
+        st = launch_envlight_query_bwd(chain, n, dirs, roughness, dL_dout, dL_ddirs, dL_droughness, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("envlight_query_bwd", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_depth_normal_forward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
                               const float* host_origin, const float* allmap, float* surf_depth, float* surf_normal,
                               void* stream_) {

@@ -12,6 +12,8 @@
 // texel centres at (i+0.5)/size, u*size-0.5 taps, LUT taps clamped, cube taps that leave a face
 // continue on the adjacent face, the missing tap at a cube corner is the mean of the other three,
 // mip level = clamp(bias, 0, L-1) with linear blending between floor and floor+1.
+#include <algorithm>
+
 #include "cube_sample.cuh"
 #include "kernels.cuh"
 
@@ -185,6 +187,18 @@ __device__ __forceinline__ void scatter_bilinear(float* __restrict__ grad_tex, c
     }
 }
 
+// gradient of the face coordinates (u, v) back to the direction: u = su*a*m + .5, v = sv*b*m + .5, m = .5/|c|
+__device__ __forceinline__ void face_uv_backward(const FaceUV& f, F3 d, float g_u, float g_v, float g_d[3]) {
+    g_d[0] = g_d[1] = g_d[2] = 0.f;
+    const float dv[3] = {d.x, d.y, d.z};
+    const float a = dv[f.ia], b = dv[f.ib], c = dv[f.ic];
+    const bool u_free = f.u > 0.f && f.u < 1.f, v_free = f.v > 0.f && f.v < 1.f;
+    const float gu = u_free ? g_u : 0.f, gv = v_free ? g_v : 0.f;
+    g_d[f.ia] += gu * f.su * f.m;
+    g_d[f.ib] += gv * f.sv * f.m;
+    g_d[f.ic] += -(gu * f.su * a + gv * f.sv * b) * f.m / fabsf(c) * f.csign;
+}
+
 __global__ void __launch_bounds__(256) shade_bwd_kernel(const MrgsShadeArgs p) {
     const int x = blockIdx.x * 32 + (threadIdx.x & 31);
     const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
@@ -240,18 +254,8 @@ __global__ void __launch_bounds__(256) shade_bwd_kernel(const MrgsShadeArgs p) {
         g_u = dot(g_t, s.b0.dval_du);
         g_v = dot(g_t, s.b0.dval_dv);
     }
-    // u = su*a*m + .5, v = sv*b*m + .5, m = .5/|c|
-    float g_rr[3] = {0.f, 0.f, 0.f};
-    {
-        const float rrv[3] = {s.rr.x, s.rr.y, s.rr.z};
-        const float a = rrv[s.fuv.ia], b = rrv[s.fuv.ib], c = rrv[s.fuv.ic];
-        const float m = s.fuv.m;
-        const bool u_free = s.fuv.u > 0.f && s.fuv.u < 1.f, v_free = s.fuv.v > 0.f && s.fuv.v < 1.f;
-        const float gu = u_free ? g_u : 0.f, gv = v_free ? g_v : 0.f;
-        g_rr[s.fuv.ia] += gu * s.fuv.su * m;
-        g_rr[s.fuv.ib] += gv * s.fuv.sv * m;
-        g_rr[s.fuv.ic] += -(gu * s.fuv.su * a + gv * s.fuv.sv * b) * m / fabsf(c) * s.fuv.csign;
-    }
+    float g_rr[3];
+    face_uv_backward(s.fuv, s.rr, g_u, g_v, g_rr);
     // rr = r / max(|r|, eps)
     F3 g_r = {0.f, 0.f, 0.f};
     {
@@ -315,12 +319,89 @@ envlight_query_kernel(const MrgsShadeArgs p, long long n, const float* __restric
     out[3 * i + 2] = sigmoidf(t.z);
 }
 
-int validate(const MrgsShadeArgs* a, const char* who, bool need_maps) {
+// Backward of envlight_query_kernel: texel gradients (float4 per texel, like shade_bwd), and optionally the
+// gradients of the directions and of the roughness. SMALL: the chain is ONE level of <= kSmallTexels texels (the
+// 6x16x16 diffuse map every surfel of render_volume samples): gradients are summed in shared memory and each CTA
+// adds its tile to global memory once, instead of n x 4 atomics on the same 1536 addresses.
+constexpr int kSmallTexels = 6 * 16 * 16;
+
+template <bool SMALL>
+__global__ void __launch_bounds__(256)
+envlight_query_bwd_kernel(const MrgsShadeArgs p, long long n, const float* __restrict__ dirs,
+                          const float* __restrict__ roughness, const float* __restrict__ dL_dout,
+                          float* __restrict__ dL_ddirs, float* __restrict__ dL_droughness) {
+    __shared__ float s_acc[SMALL ? kSmallTexels * 3 : 1];
+    const int texels0 = 6 * p.base_res * p.base_res;
+    if (SMALL) {
+        for (int k = threadIdx.x; k < texels0 * 3; k += blockDim.x) s_acc[k] = 0.f;
+        __syncthreads();
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const F3 d = {dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]};
+        const FaceUV f = dir_to_face(d);
+        Bilinear b0, b1;
+        MipLevel m;
+        m.l0 = m.l1 = 0;
+        m.f = 0.f;
+        m.dlevel_drough = 0.f;
+        if (roughness != nullptr) m = rough_to_level(roughness[i], p.min_roughness, p.max_roughness, p.num_levels);
+        cube_bilinear<true>(p.levels[m.l0], p.base_res >> m.l0, f.face, f.u, f.v, b0);
+        F3 t = b0.val;
+        const bool two = m.l1 != m.l0;
+        if (two) {
+            cube_bilinear<true>(p.levels[m.l1], p.base_res >> m.l1, f.face, f.u, f.v, b1);
+            t = (1.0f - m.f) * b0.val + m.f * b1.val;
+        }
+        const F3 o = {sigmoidf(t.x), sigmoidf(t.y), sigmoidf(t.z)};
+        const F3 g = {dL_dout[3 * i], dL_dout[3 * i + 1], dL_dout[3 * i + 2]};
+        const F3 g_t = {g.x * o.x * (1.0f - o.x), g.y * o.y * (1.0f - o.y), g.z * o.z * (1.0f - o.z)};
+        float g_u, g_v;
+        if (two) {
+            if (p.dL_dlevels[m.l0]) scatter_bilinear(p.dL_dlevels[m.l0], b0, (1.0f - m.f) * g_t);
+            if (p.dL_dlevels[m.l1]) scatter_bilinear(p.dL_dlevels[m.l1], b1, m.f * g_t);
+            if (dL_droughness) dL_droughness[i] = dot(g_t, b1.val - b0.val) * m.dlevel_drough;
+            g_u = dot(g_t, (1.0f - m.f) * b0.dval_du + m.f * b1.dval_du);
+            g_v = dot(g_t, (1.0f - m.f) * b0.dval_dv + m.f * b1.dval_dv);
+        } else {
+            if (SMALL) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    if (b0.idx[k] < 0 || b0.w[k] == 0.f) continue;
+                    atomicAdd(&s_acc[3 * b0.idx[k] + 0], b0.w[k] * g_t.x);
+                    atomicAdd(&s_acc[3 * b0.idx[k] + 1], b0.w[k] * g_t.y);
+                    atomicAdd(&s_acc[3 * b0.idx[k] + 2], b0.w[k] * g_t.z);
+                }
+            } else if (p.dL_dlevels[m.l0]) {
+                scatter_bilinear(p.dL_dlevels[m.l0], b0, g_t);
+            }
+            if (dL_droughness) dL_droughness[i] = 0.f;
+            g_u = dot(g_t, b0.dval_du);
+            g_v = dot(g_t, b0.dval_dv);
+        }
+        if (dL_ddirs) {
+            float g_d[3];
+            face_uv_backward(f, d, g_u, g_v, g_d);
+            dL_ddirs[3 * i] = g_d[0];
+            dL_ddirs[3 * i + 1] = g_d[1];
+            dL_ddirs[3 * i + 2] = g_d[2];
+        }
+    }
+    if (SMALL) {
+        __syncthreads();
+        float4* out = reinterpret_cast<float4*>(p.dL_dlevels[0]);
+        for (int k = threadIdx.x; k < texels0; k += blockDim.x) {
+            const float x = s_acc[3 * k], y = s_acc[3 * k + 1], z = s_acc[3 * k + 2];
+            if (x != 0.f || y != 0.f || z != 0.f) atomicAdd(out + k, make_float4(x, y, z, 0.f));
+        }
+    }
+}
+
+int validate(const MrgsShadeArgs* a, const char* who, bool need_maps, int min_levels = 2) {
     if (a == nullptr) {
         set_error("%s: null args", who);
         return MRGS_ERR_INVALID_ARGUMENT;
     }
-    if (a->num_levels < 2 || a->num_levels > MRGS_MAX_MIP_LEVELS || a->base_res <= 0 ||
+    if (a->num_levels < min_levels || a->num_levels > MRGS_MAX_MIP_LEVELS || a->base_res <= 0 ||
         (a->base_res >> (a->num_levels - 1)) < 1) {
         set_error("%s: bad mip chain (levels=%d, base_res=%d)", who, a->num_levels, a->base_res);
         return MRGS_ERR_INVALID_ARGUMENT;
@@ -352,10 +433,27 @@ int launch_shade(const MrgsShadeArgs* a, bool backward, cudaStream_t stream) {
 
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream) {
-    int st = validate(a, "mrgs_envlight_query", false);
+    int st = validate(a, "mrgs_envlight_query", false, roughness ? 2 : 1);
     if (st != MRGS_OK) return st;
     if (n <= 0) return MRGS_OK;
     envlight_query_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(*a, n, dirs, roughness, out);
+    return MRGS_OK;
+}
+
+int launch_envlight_query_bwd(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
+                              const float* dL_dout, float* dL_ddirs, float* dL_droughness, cudaStream_t stream) {
+    int st = validate(a, "mrgs_envlight_query_backward", false, roughness ? 2 : 1);
+    if (st != MRGS_OK) return st;
+    if (n <= 0) return MRGS_OK;
+    const bool small = roughness == nullptr && a->dL_dlevels[0] != nullptr && 6 * a->base_res * a->base_res <= kSmallTexels;
+    if (small) {
+        // few, fat CTAs: every CTA flushes its shared-memory tile once
+        const unsigned blocks = (unsigned)std::min<long long>((n + 255) / 256, 148 * 4);
+        envlight_query_bwd_kernel<true><<<blocks, 256, 0, stream>>>(*a, n, dirs, roughness, dL_dout, dL_ddirs, dL_droughness);
+    } else {
+        envlight_query_bwd_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(*a, n, dirs, roughness, dL_dout,
+                                                                                        dL_ddirs, dL_droughness);
+    }
     return MRGS_OK;
 }
 

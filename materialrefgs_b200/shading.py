@@ -46,9 +46,9 @@ def _stream(dev):
     return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
-def _chain_args(levels, min_roughness, max_roughness) -> _lib.ShadeArgs:
-    if not 2 <= len(levels) <= _lib.MAX_MIP_LEVELS:
-        raise RuntimeError(f"mip chain must have 2..{_lib.MAX_MIP_LEVELS} levels, got {len(levels)}")
+def _chain_args(levels, min_roughness, max_roughness, min_levels: int = 2) -> _lib.ShadeArgs:
+    if not min_levels <= len(levels) <= _lib.MAX_MIP_LEVELS:
+        raise RuntimeError(f"mip chain must have {min_levels}..{_lib.MAX_MIP_LEVELS} levels, got {len(levels)}")
     a = _lib.ShadeArgs()
     a.num_levels = len(levels)
     a.base_res = int(levels[0].shape[1])
@@ -237,6 +237,60 @@ def get_specular_color_surfel(envmap: "EnvLight", albedo, HWK, R, T, normal_map,
     return specular, extra
 
 
+def safe_normalize(x, eps=1e-20):
+    return x / torch.clamp(torch.linalg.norm(x, dim=-1, keepdim=True), min=eps)   # utils/general_utils.py:179-182
+
+
+def _camera_origin(R, T, device):
+    """rays_o of sample_camera_rays (utils/refl_utils.py:56, :68): -R @ T with the c2w rotation 3DGS cameras store."""
+    R = torch.as_tensor(np.asarray(R.detach().cpu() if isinstance(R, torch.Tensor) else R), dtype=torch.float32, device=device)
+    T = torch.as_tensor(np.asarray(T.detach().cpu() if isinstance(T, torch.Tensor) else T), dtype=torch.float32, device=device)
+    return (-R @ T.unsqueeze(-1)).flatten()
+
+
+def _fg_of_first_surfel(ndotv, roughness):
+    """The FG pair get_full_color_volume applies to EVERY surfel: the reference fetches the LUT for all N surfels and
+    then indexes `fg[0]` on the [N,2] result (utils/refl_utils.py:437-445, :474-481), i.e. the first surfel's pair
+    (kept as is). dr.texture(filter_mode='linear', boundary_mode='clamp') == bilinear with border clamping."""
+    uv = torch.cat([ndotv[0:1], roughness[0:1]], -1).clamp(0, 1)
+    lut = fg_lut(uv.device)[None]                             # [1,256,256,2]
+    grid = (uv * 2.0 - 1.0).reshape(1, 1, 1, 2)
+    fg = torch.nn.functional.grid_sample(lut.permute(0, 3, 1, 2), grid, mode="bilinear", padding_mode="border",
+                                         align_corners=False)
+    return fg[0, :, 0, 0]                                     # [2]
+
+
+def get_full_color_volume(envmap: "EnvLight", xyz, albedo, HWK, R, T, normal_map, render_alpha, scaling_modifier=1.0,
+                          refl_strength=None, roughness=None):
+    """utils/refl_utils.py:426-447 — per-SURFEL split-sum colours (the volume-rendering stage): (diffuse, specular) [N,3]."""
+    rays_o = _camera_origin(R, T, xyz.device).expand(normal_map.shape[0], -1)
+    w_o = safe_normalize(rays_o - xyz)
+    NdotV = torch.sum(w_o * normal_map, dim=-1, keepdim=True)
+    rays_refl = safe_normalize(2 * normal_map * NdotV - w_o)
+    fg = _fg_of_first_surfel(NdotV, roughness)
+    diffuse = envmap(normal_map, mode="diffuse") * (1 - refl_strength) * albedo
+    specular = envmap(rays_refl, roughness=roughness) * ((0.04 * (1 - refl_strength) + albedo * refl_strength) * fg[0:1] + fg[1:2])
+    return diffuse, specular
+
+
+def get_full_color_volume_indirect(envmap: "EnvLight", xyz, albedo, HWK, R, T, normal_map, render_alpha,
+                                   scaling_modifier=1.0, refl_strength=None, roughness=None, pc=None, indirect_light=None):
+    """utils/refl_utils.py:450-490 with visibility = 1 (the mesh/OptiX tracer stays on the reference)."""
+    if pc is not None and getattr(pc, "ray_tracer", None) is not None:
+        raise NotImplementedError("mesh/OptiX visibility tracing stays on the reference")
+    rays_o = _camera_origin(R, T, xyz.device).expand(normal_map.shape[0], -1)
+    w_o = safe_normalize(rays_o - xyz)
+    NdotV = torch.sum(w_o * normal_map, dim=-1, keepdim=True)
+    rays_refl = safe_normalize(2 * normal_map * NdotV - w_o)
+    visibility = torch.ones_like(render_alpha)
+    fg = _fg_of_first_surfel(NdotV, roughness)
+    diffuse = envmap(normal_map, mode="diffuse") * (1 - refl_strength) * albedo
+    direct_light = envmap(rays_refl, roughness=roughness)
+    specular_weight = (0.04 * (1 - refl_strength) + albedo * refl_strength) * fg[0:1] + fg[1:2]
+    specular_light = direct_light * visibility + (1 - visibility) * indirect_light
+    return diffuse, specular_light * specular_weight, {"visibility": visibility, "direct_light": direct_light}
+
+
 class EnvLight(torch.nn.Module):
     """Trainable logit-space cubemap with a GGX-prefiltered mip chain (scene/light.py:21-129)."""
 
@@ -281,30 +335,72 @@ class EnvLight(torch.nn.Module):
             / (1.0 - self.max_roughness) + n - 2)
 
     def forward(self, l, mode=None, roughness=None):
-        """Query the environment light for directions l[..., 3] (forward only; gradients reach the
-        cubemap through shade_surfel)."""
-        lib = _lib.load()
+        """Query the environment light for directions l[..., 3] (scene/light.py:98-129): "diffuse" samples the
+        cosine-convolved 16^2 map, "pure_env" the base level, otherwise the GGX chain at get_mip(roughness).
+        Differentiable like dr.texture: gradients reach the mip levels (and through build_mips the base cubemap),
+        the directions and the roughness."""
         prefix = l.shape[:-1]
-        d = l.detach().reshape(-1, 3).contiguous().float()
-        out = torch.empty_like(d)
         if mode == "diffuse":
-            levels = [self.diffuse]
+            levels, rough = [self.diffuse], None
         elif mode == "pure_env":
-            levels = [self.base]
+            levels, rough = [self.base], None
         else:
-            levels = self.specular
-        rough = None
-        if mode not in ("diffuse", "pure_env") and roughness is not None:
-            rough = roughness.detach().reshape(-1).contiguous().float()
-        if len(levels) == 1:  # the ABI wants >= 2 levels; duplicate is never read without roughness
-            small = torch.nn.functional.avg_pool2d(levels[0].detach().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1).contiguous()
-            levels = [levels[0].detach().contiguous(), small]
-        a = _chain_args([x.detach().contiguous() for x in levels], self.min_roughness, self.max_roughness)
-        with torch.cuda.device(d.device):
-            _lib.check(lib.mrgs_envlight_query(C.byref(a), d.shape[0], d.data_ptr(),
-                                               None if rough is None else rough.data_ptr(), out.data_ptr(),
-                                               _stream(d.device)), "mrgs_envlight_query")
+            levels, rough = self.specular, roughness
+        out = _EnvQuery.apply(l.reshape(-1, 3), None if rough is None else rough.reshape(-1),
+                              (self.min_roughness, self.max_roughness), *levels)
         return out.view(*prefix, 3)
+
+
+class _EnvQuery(torch.autograd.Function):
+    """(dirs [n,3], roughness [n] or None, *levels) -> sigmoid(cube fetch) [n,3]; mrgs_envlight_query(+_backward)."""
+
+    @staticmethod
+    def forward(ctx, dirs, roughness, cfg, *levels):
+        lib = _lib.load()
+        if not dirs.is_cuda:
+            raise RuntimeError("EnvLight: directions must be a CUDA tensor")
+        d = dirs.detach().contiguous().float()
+        r = None if roughness is None else roughness.detach().contiguous().float()
+        lv = [x.detach().contiguous() for x in levels]
+        a = _chain_args(lv, cfg[0], cfg[1], min_levels=1 if r is None else 2)
+        out = torch.empty_like(d)
+        with torch.cuda.device(d.device):
+            _lib.check(lib.mrgs_envlight_query(C.byref(a), d.shape[0], d.data_ptr(), None if r is None else r.data_ptr(),
+                                               out.data_ptr(), _stream(d.device)), "mrgs_envlight_query")
+        ctx.cfg, ctx.has_rough = cfg, r is not None
+        ctx.save_for_backward(d, *([r] if r is not None else []), *lv)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        lib = _lib.load()
+        d, *rest = ctx.saved_tensors
+        r = rest.pop(0) if ctx.has_rough else None
+        lv = rest
+        dev = d.device
+        a = _chain_args(lv, ctx.cfg[0], ctx.cfg[1], min_levels=1 if r is None else 2)
+        need_d, need_r = ctx.needs_input_grad[0], ctx.has_rough and ctx.needs_input_grad[1]
+        need_l = [ctx.needs_input_grad[3 + i] for i in range(len(lv))]
+        g = g_out.contiguous().float()
+        g_d = torch.empty_like(d) if need_d else None
+        g_r = torch.empty_like(r) if need_r else None
+        counts = [x.shape[0] * x.shape[1] * x.shape[2] for x in lv]
+        flat4 = torch.zeros((sum(counts), 4), dtype=torch.float32, device=dev) if any(need_l) else None
+        off = 0
+        for i, n in enumerate(counts):
+            if need_l[i]:
+                a.dL_dlevels[i] = flat4.data_ptr() + off * 16
+            off += n
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_envlight_query_backward(
+                C.byref(a), d.shape[0], d.data_ptr(), None if r is None else r.data_ptr(), g.data_ptr(),
+                None if g_d is None else g_d.data_ptr(), None if g_r is None else g_r.data_ptr(), _stream(dev)),
+                "mrgs_envlight_query_backward")
+        g_levels, off = [], 0
+        for x, n, need in zip(lv, counts, need_l):
+            g_levels.append(flat4[off:off + n, :3].reshape(x.shape) if need else None)
+            off += n
+        return (g_d, g_r, None, *g_levels)
 
 
 def smoke_check(dev) -> None:

@@ -11,6 +11,7 @@ tap replaced by the mean of the other three, mip level = clamp(bias,0,L-1) blend
 What it follows:
   sample_camera_rays / reflection          utils/refl_utils.py:54-73, :95-98
   get_specular_color_surfel (visibility=1) utils/refl_utils.py:364-419
+  get_full_color_volume                    utils/refl_utils.py:426-447
   EnvLight.get_mip / __call__              scene/light.py:88-129
   render_surfel compositing                gaussian_renderer/__init__.py:372-376, :419-420, :433-445
   compute_2dgs_normal_and_regularizations  gaussian_renderer/__init__.py:42-48 (normal to world)
@@ -153,8 +154,9 @@ def cubemap_mip(cubemap):  # scene/light_utils.py:66-70 (forward)
 class EnvLightOracle:
     """scene/light.py:21-129 with a caller-provided mip chain (logit space)."""
 
-    def __init__(self, levels, min_roughness=0.08, max_roughness=0.5):
+    def __init__(self, levels, min_roughness=0.08, max_roughness=0.5, diffuse=None):
         self.specular = list(levels)
+        self.diffuse = diffuse          # the cosine-convolved last level (scene/light.py:79), [6,16,16,3]
         self.min_roughness, self.max_roughness = min_roughness, max_roughness
 
     def get_mip(self, roughness):  # scene/light.py:88-96
@@ -169,7 +171,9 @@ class EnvLightOracle:
     def __call__(self, l, mode=None, roughness=None):  # scene/light.py:98-129
         prefix = l.shape[:-1]
         d = l.reshape(-1, 3)
-        if mode in ("diffuse", "pure_env") or roughness is None:
+        if mode == "diffuse" and self.diffuse is not None:   # scene/light.py:108-110
+            light = cube_texture([self.diffuse], d)
+        elif mode in ("diffuse", "pure_env") or roughness is None:
             light = cube_texture(self.specular, d)
         else:
             light = cube_texture(self.specular, d, self.get_mip(roughness.reshape(-1)))
@@ -198,6 +202,21 @@ def get_specular_color_surfel(envmap, lut, albedo, HWK, R, T, normal_map, render
     specular = direct_light * render_alpha * specular_weight
     return specular.permute(2, 0, 1), {"direct_light": direct_light.permute(2, 0, 1),
                                        "specular_weight": specular_weight}
+
+
+def get_full_color_volume(envmap, lut, xyz, albedo, cam, normal_map, refl_strength, roughness):
+    """utils/refl_utils.py:426-447: per-surfel split-sum colours of the volume-rendering stage. The reference fetches
+    the LUT for all N surfels, squeezes the result to [N,2] and then indexes `fg[0]` (:445): the FIRST surfel's
+    (scale, bias) pair multiplies every surfel. Restated as written."""
+    _, rays_o = sample_camera_rays(cam.HWK, cam.R, cam.T, xyz.device)
+    w_o = safe_normalize(rays_o.expand(normal_map.shape[0], -1) - xyz)
+    NdotV = torch.sum(w_o * normal_map, dim=-1, keepdim=True)          # reflection(), :95-98
+    rays_refl = safe_normalize(2 * normal_map * NdotV - w_o)
+    fg = lut_fetch(lut, torch.cat([NdotV, roughness], -1).clamp(0, 1))  # [N,2]
+    diffuse = envmap(normal_map, mode="diffuse") * (1 - refl_strength) * albedo
+    specular = envmap(rays_refl, roughness=roughness) * (
+        (0.04 * (1 - refl_strength) + albedo * refl_strength) * fg[0][..., 0:1] + fg[0][..., 1:2])
+    return diffuse, specular
 
 
 def shade_surfel(envmap, lut, rendered_image, rendered_features, allmap, cam, bg_color, srgb=False):

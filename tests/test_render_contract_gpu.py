@@ -196,3 +196,126 @@ def test_render_surfel_contract_raw_parameters(ref_ext):
         l1 = ((a - b).abs().sum() / b.abs().sum().clamp_min(1e-20)).item()
         out_frac = ((a - b).abs() > 1e-2 * b.abs().max()).float().mean().item()
         assert l1 <= 5e-3 and out_frac <= 1e-3, (k, l1, out_frac)
+
+
+# ---- render_initial / render_volume (gaussian_renderer/__init__.py:94-222, :521-745) -----------------------------
+def _raster_ref(ref_ext, cam, bg, **kw):
+    rs = ref_ext.GaussianRasterizationSettings(
+        cam.image_height, cam.image_width, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), torch.zeros_like(bg), 1.0,
+        cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center, False, False)
+    return ref_ext.GaussianRasterizer(rs)(**kw)
+
+
+def _regularizations(allmap, cam, pipe):
+    out = {"rend_alpha": allmap[1:2], "rend_dist": allmap[6:7],
+           "rend_normal": (allmap[2:5].permute(1, 2, 0) @ cam.world_view_transform[:3, :3].T).permute(2, 0, 1)}
+    out["surf_depth"], out["surf_normal"] = so.surf_depth_normal(allmap, cam, pipe.depth_ratio)
+    return out
+
+
+def _close_grads(ga, gb, name):
+    l1 = ((ga - gb).abs().sum() / gb.abs().sum().clamp_min(1e-20)).item()
+    out_frac = ((ga - gb).abs() > 1e-2 * gb.abs().max()).float().mean().item()
+    assert l1 <= 5e-3 and out_frac <= 1e-3, (name, l1, out_frac)
+
+
+def test_render_initial_contract(ref_ext):
+    from materialrefgs_b200.render import render_initial
+    W, H, P = 333, 200, 30_000
+    cloud = synthetic.make_cloud(P, S=5, seed=41).to(DEV)
+    cam = synthetic.orbit_camera(3, 8, W, H).to(DEV)
+    pipe = types.SimpleNamespace(debug=False, depth_ratio=1.0, compute_cov3D_python=False)
+    bg = torch.tensor([0.0, 0.5, 1.0], device=DEV)
+    g = torch.Generator().manual_seed(14)
+    wts = {k: (torch.randn(c, H, W, generator=g) / (H * W)).to(DEV)
+           for k, c in (("render", 3), ("rend_normal", 3), ("surf_normal", 3), ("rend_dist", 1), ("surf_depth", 1))}
+    loss_of = lambda o: sum((o[k] * w).sum() for k, w in wts.items())
+
+    pc = FakeModel(cloud, None)
+    out = render_initial(cam, pc, pipe, bg, srgb=True)
+    assert set(out) == {"render", "viewspace_points", "visibility_filter", "radii", "rend_alpha", "rend_normal", "rend_dist",
+                        "surf_depth", "surf_normal"}
+    loss_of(out).backward()
+
+    pc2 = FakeModel(cloud, None)
+    m2d = torch.zeros_like(pc2.get_xyz, requires_grad=True)
+    _, color, _, radii, allmap = _raster_ref(ref_ext, cam, bg, means3D=pc2.get_xyz, means2D=m2d, opacities=pc2.get_opacity,
+                                             shs=pc2.get_features, features=torch.empty((P, 0)), scales=pc2.get_scaling,
+                                             rotations=pc2.get_rotation)
+    ref = _regularizations(allmap, cam, pipe)
+    ref["render"] = so.linear_to_srgb(color) + bg[:, None, None] * (1 - ref["rend_alpha"])
+    loss_of(ref).backward()
+    assert torch.equal(out["radii"], radii)
+    for k in wts:
+        assert (out[k] - ref[k]).abs().max().item() <= (5e-4 if k == "surf_normal" else 1e-4), k
+    for k in ("means3D", "scales", "rotations", "opacities", "shs"):
+        _close_grads(pc.leaves[k].grad, pc2.leaves[k].grad, k)
+
+
+@pytest.mark.parametrize("indirect", [False, True])
+def test_render_volume_contract(ref_ext, indirect):
+    """Per-surfel shading through the differentiable EnvLight queries + S = 11 / 18 feature channels."""
+    from materialrefgs_b200.render import render_volume
+    from materialrefgs_b200.shading import EnvLight
+    W, H, P = 256, 192, 25_000
+    cloud = synthetic.make_cloud(P, S=5, seed=43).to(DEV)
+    cam = synthetic.orbit_camera(6, 8, W, H).to(DEV)
+    env = EnvLight(device=DEV, max_res=64, min_res=16, trainable=True)
+    with torch.no_grad():
+        env.base.copy_(torch.randn(6, 64, 64, 3, generator=torch.Generator().manual_seed(4)).to(DEV))
+    pipe = types.SimpleNamespace(debug=False, depth_ratio=0.0, compute_cov3D_python=False, use_asg=False)
+    opt = types.SimpleNamespace(indirect=indirect)
+    bg = torch.tensor([0.3, 0.2, 0.1], device=DEV)
+    g = torch.Generator().manual_seed(15)
+    keys = [("render", 3), ("diffuse_map", 3), ("specular_map", 3), ("base_color_map", 3), ("roughness_map", 1),
+            ("refl_strength_map", 1), ("rend_normal", 3), ("surf_normal", 3)] + ([("direct_light", 3), ("indirect_light", 3)] if indirect else [])
+    wts = {k: (torch.randn(c, H, W, generator=g) / (H * W)).to(DEV) for k, c in keys}
+    loss_of = lambda o: sum((o[k] * w).sum() for k, w in wts.items())
+
+    class VolumeModel(FakeModel):
+        get_envmap_2 = property(lambda s: s.env)
+        ray_tracer = None
+
+    env.build_mips()
+    pc = VolumeModel(cloud, env)
+    out = render_volume(cam, pc, pipe, bg, opt=opt)
+    loss_of(out).backward()
+    g_env = env.base.grad.clone()
+
+    env.base.grad = None
+    env.build_mips()
+    pc2 = VolumeModel(cloud, env)
+    oracle_env = so.EnvLightOracle(list(env.specular), diffuse=env.diffuse)
+    d = pc2.get_xyz - cam.camera_center
+    d = d / d.norm(dim=1, keepdim=True)
+    n = pc2.get_normal(1.0, d)
+    refl_dir = 2 * torch.sum(n * -d, dim=1, keepdim=True) * n + d
+    ind = torch.clamp_min(eval_sh(3, pc2.get_indirect.transpose(1, 2).view(-1, 3, 16), refl_dir), 0.0)
+    diffuse, specular = so.get_full_color_volume(oracle_env, so.load_lut(DEV), pc2.get_xyz, pc2.get_ori_color, cam, n,
+                                                 pc2.get_refl, pc2.get_rough)
+    feats = [pc2.get_rough, pc2.get_refl, diffuse, specular, pc2.get_ori_color]
+    if indirect:   # visibility = 1 without a tracer: specular_light = direct_light (refl_utils.py:460-484)
+        w_o = so.safe_normalize(cam.camera_center.expand(P, -1) - pc2.get_xyz)
+        rr = so.safe_normalize(2 * n * torch.sum(w_o * n, -1, keepdim=True) - w_o)
+        feats += [torch.ones_like(pc2.get_opacity), ind, oracle_env(rr, roughness=pc2.get_rough)]
+    m2d = torch.zeros_like(pc2.get_xyz, requires_grad=True)
+    _, color, feat, radii, allmap = _raster_ref(ref_ext, cam, bg, means3D=pc2.get_xyz, means2D=m2d, opacities=pc2.get_opacity,
+                                                colors_precomp=specular + diffuse, features=torch.cat(feats, -1),
+                                                scales=pc2.get_scaling, rotations=pc2.get_rotation)
+    ref = _regularizations(allmap, cam, pipe)
+    ref.update({"render": color + bg[:, None, None] * (1 - ref["rend_alpha"]), "roughness_map": feat[:1],
+                "refl_strength_map": feat[1:2], "diffuse_map": feat[2:5], "specular_map": feat[5:8], "base_color_map": feat[8:11]})
+    if indirect:
+        ref.update({"visibility": feat[11:12], "indirect_light": feat[12:15], "direct_light": feat[15:18]})
+    loss_of(ref).backward()
+
+    assert torch.equal(out["radii"], radii)
+    for k in wts:
+        assert (out[k] - ref[k]).abs().max().item() <= (5e-4 if k == "surf_normal" else 1e-4), k
+    if indirect:
+        assert (out["visibility"] - ref["visibility"]).abs().max().item() <= 1e-4
+    for k in ("means3D", "scales", "rotations", "opacities", "features"):
+        _close_grads(pc.leaves[k].grad, pc2.leaves[k].grad, k)
+    _close_grads(g_env, env.base.grad, "envmap")
+    if indirect:
+        _close_grads(pc.ind.grad, pc2.ind.grad, "indirect")

@@ -131,3 +131,67 @@ def test_surf_depth_and_depth_to_normal(ratio, H, W):
         ref = a_o.grad[pl][ok]
         assert ((a_m.grad[pl][ok] - ref).abs().max() / ref.abs().max().clamp_min(1e-20)).item() <= 2e-3, pl
     assert not a_m.grad[[2, 3, 4, 6]].any()
+
+
+# ---- differentiable EnvLight.__call__ (mrgs_envlight_query / _backward) -----------------------------------------
+def _query_dirs(n, seed):
+    g = torch.Generator().manual_seed(seed)
+    d = torch.randn(n, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    # a share of directions hugging cube edges and corners (seamless taps, 3-texel corner average)
+    k = n // 8
+    d[:k, 0] = d[:k, 1] * (1 + 1e-3 * torch.randn(k, generator=g))
+    d[k:2 * k] = torch.sign(d[k:2 * k]) * (1 + 2e-2 * torch.rand(k, 3, generator=g))
+    return d * (0.5 + torch.rand(n, 1, generator=g))          # un-normalised: dr.texture does not normalise either
+
+
+@pytest.mark.parametrize("mode,res", [(None, 64), ("diffuse", 16), ("pure_env", 64), ("diffuse", 32)])
+def test_envlight_query_forward_backward(mode, res):
+    n = 20_000
+    levels = so.synthetic_chain(64, 16, device=DEV)
+    diffuse = 0.7 * torch.randn(6, res, res, 3, generator=torch.Generator().manual_seed(8)).to(DEV)
+    d0 = _query_dirs(n, 5).to(DEV)
+    r0 = (torch.rand(n, 1, generator=torch.Generator().manual_seed(6)) * 1.3 - 0.15).to(DEV)   # beyond both clamps
+    w = torch.randn(n, 3, generator=torch.Generator().manual_seed(7)).to(DEV)
+
+    def run(make_env):
+        lv = [l.clone().requires_grad_(True) for l in levels]
+        df = diffuse.clone().requires_grad_(True)
+        d, r = d0.clone().requires_grad_(True), r0.clone().requires_grad_(True)
+        out = make_env(lv, df)(d, mode=mode, roughness=None if mode else r)
+        (out * w).sum().backward()
+        return out.detach(), d.grad, r.grad, [l.grad for l in lv], df.grad
+
+    def ours(lv, df):
+        env = _env(lv)
+        env.diffuse, env.base = df, lv[0]
+        return env
+    o_out, o_d, o_r, o_lv, o_df = run(ours)
+    r_out, r_d, r_r, r_lv, r_df = run(lambda lv, df: so.EnvLightOracle(lv, diffuse=df))
+    assert o_out.shape == (n, 3) and (o_out - r_out).abs().max().item() <= 1e-5
+    # direction gradients are piecewise (texel cells): compare by relative L1 with a bound on outliers
+    l1 = ((o_d - r_d).abs().sum() / r_d.abs().sum()).item()
+    assert l1 <= 2e-3 and ((o_d - r_d).abs() > 1e-2 * r_d.abs().max()).float().mean().item() <= 1e-3
+    if mode is None:
+        l1r = ((o_r - r_r).abs().sum() / r_r.abs().sum()).item()
+        assert l1r <= 2e-3
+        for a, b in zip(o_lv, r_lv):
+            assert _rel(a, b) <= 1e-3
+        assert o_df is None
+    elif mode == "diffuse":
+        assert _rel(o_df, r_df) <= 1e-3 and all(g is None for g in o_lv) and o_r is None
+    else:
+        assert _rel(o_lv[0], r_lv[0]) <= 1e-3 and all(g is None for g in o_lv[1:])
+
+
+def test_envlight_query_keeps_leading_shape_and_reaches_the_base_cubemap():
+    from materialrefgs_b200.shading import EnvLight
+    env = EnvLight(device=DEV, max_res=64, min_res=16, trainable=True)   # 3 levels (2 would divide by zero, as in light.py:82)
+    with torch.no_grad():
+        env.base.copy_(torch.randn(6, 64, 64, 3, generator=torch.Generator().manual_seed(1)).to(DEV))
+    env.build_mips()
+    d = _query_dirs(4 * 5 * 6, 2).view(4, 5, 6, 3).to(DEV)
+    out = env(d, roughness=torch.full((4, 5, 6, 1), 0.3, device=DEV)) + env(d, mode="diffuse")
+    assert out.shape == (4, 5, 6, 3)
+    out.sum().backward()
+    assert env.base.grad is not None and env.base.grad.abs().sum().item() > 0
