@@ -14,6 +14,8 @@
 //     conflict-free LDS.128) and leave the warp as ONE coalesced red.global.add per instance
 //     instead of 16+S same-address atomics per pixel;
 //   * a warp skips the reduction when none of its pixels is touched by the instance.
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "splat_math.cuh"
 
@@ -25,28 +27,32 @@ constexpr unsigned kFull = 0xffffffffu;
 
 constexpr int kRedStride = 36;  // floats per value row: 32 lanes + 4 pad keeps LDS.128 conflict-free
 
-template <int NQ>
+template <int NQ, int WPC>
 constexpr int bwd_smem_bytes() {
     // per warp: 4 geometry vectors + NQ colour vectors + ids for 32 staged instances, and the
     // [NV][36] transposition buffer of the warp reduction
-    return kWarpsPerTile * ((4 + NQ) * 32 * 16 + 32 * 4 + (kGradColor + NQ * 4) * kRedStride * 4);
+    return WPC * ((4 + NQ) * 32 * 16 + 32 * 4 + (kGradColor + NQ * 4) * kRedStride * 4);
 }
 
-template <int NQ>
-__global__ void __launch_bounds__(kTilePixels, (NQ <= 3) ? 2 : 1)
+// WPC warps per CTA: the warps of a tile never synchronise with each other, so a tile can be split over 8 / WPC CTAs
+// (blockIdx.z) — the register file then holds a non-integer number of TILES per SM (e.g. 5 CTAs of 4 warps at <= 102
+// registers = 20 warps instead of 2 CTAs of 8 = 16).
+template <int NQ, int WPC, int MINB>
+__global__ void __launch_bounds__(WPC * 32, MINB)
 render_bwd_kernel(const RenderBwdParams p) {
     constexpr int NC = NQ * 4;           // colour + feature (+ padding) channels
     constexpr int NV = kGradColor + NC;  // values per instance incl. padding channels
     constexpr bool kTwoPass = NV > 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float4 (*s_g)[4][32] = reinterpret_cast<float4 (*)[4][32]>(smem_raw);
-    float4 (*s_cf)[NQ][32] = reinterpret_cast<float4 (*)[NQ][32]>(smem_raw + kWarpsPerTile * 4 * 32 * 16);
-    uint32_t (*s_id)[32] = reinterpret_cast<uint32_t (*)[32]>(smem_raw + kWarpsPerTile * (4 + NQ) * 32 * 16);
-    float* s_red = reinterpret_cast<float*>(smem_raw + kWarpsPerTile * ((4 + NQ) * 32 * 16 + 32 * 4)) +
+    float4 (*s_cf)[NQ][32] = reinterpret_cast<float4 (*)[NQ][32]>(smem_raw + WPC * 4 * 32 * 16);
+    uint32_t (*s_id)[32] = reinterpret_cast<uint32_t (*)[32]>(smem_raw + WPC * (4 + NQ) * 32 * 16);
+    float* s_red = reinterpret_cast<float*>(smem_raw + WPC * ((4 + NQ) * 32 * 16 + 32 * 4)) +
                    (threadIdx.x >> 5) * (NV * kRedStride);
 
-    const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
+    const int tid = blockIdx.z * (WPC * 32) + threadIdx.x;   // slot of this thread's pixel in the tile
+    const int lane = tid & 31, warp = tid >> 5;               // warp: which 8x4 block of the tile
+    const int lw = threadIdx.x >> 5;                          // this warp's shared-memory slot set
     const int tile = blockIdx.y * p.grid_x + blockIdx.x;
     const int px = blockIdx.x * kTileX + slot_x(tid);
     const int py = blockIdx.y * kTileY + slot_y(tid);
@@ -141,15 +147,15 @@ render_bwd_kernel(const RenderBwdParams p) {
         unsigned mask = __ballot_sync(kFull, keep);
         if (mask == 0) continue;
         if (keep) {
-            s_id[warp][lane] = id;
+            s_id[lw][lane] = id;
             const float4* r = rec4 + (size_t)id * (kGeomFloats / 4);
-            s_g[warp][0][lane] = r[0];
-            s_g[warp][1][lane] = r[1];
-            s_g[warp][2][lane] = r[2];
-            s_g[warp][3][lane] = r[3];
+            s_g[lw][0][lane] = r[0];
+            s_g[lw][1][lane] = r[1];
+            s_g[lw][2][lane] = r[2];
+            s_g[lw][3][lane] = r[3];
             const float4* c = cf4 + (size_t)id * NQ;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) s_cf[warp][q][lane] = c[q];
+            for (int q = 0; q < NQ; ++q) s_cf[lw][q][lane] = c[q];
         }
         __syncwarp();
 
@@ -157,8 +163,8 @@ render_bwd_kernel(const RenderBwdParams p) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
             const int e = hi - 1 - j;
-            const float4 g0 = s_g[warp][0][j], g1 = s_g[warp][1][j], g2 = s_g[warp][2][j];
-            const float4 g3 = s_g[warp][3][j];
+            const float4 g0 = s_g[lw][0][j], g1 = s_g[lw][1][j], g2 = s_g[lw][2][j];
+            const float4 g3 = s_g[lw][3][j];
             SplatHit h;
             const bool valid = (e < last_contributor) && ray_splat(g0, g1, g2, g3.w, pxf, pyf, h);
             if (!__any_sync(kFull, valid)) continue;
@@ -180,7 +186,7 @@ render_bwd_kernel(const RenderBwdParams p) {
                     float2 dot2 = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
-                        const float4 cv = s_cf[warp][k][j];
+                        const float4 cv = s_cf[lw][k][j];
                         dot2 = __ffma2_rn(make_float2(cv.x, cv.y), dL_dpix[2 * k], dot2);
                         dot2 = __ffma2_rn(make_float2(cv.z, cv.w), dL_dpix[2 * k + 1], dot2);
                         const float2 ga = __fmul2_rn(w2, dL_dpix[2 * k]), gb = __fmul2_rn(w2, dL_dpix[2 * k + 1]);
@@ -255,7 +261,7 @@ render_bwd_kernel(const RenderBwdParams p) {
 #pragma unroll
             for (int c = 0; c < NV; ++c) s_red[c * kRedStride + lane] = v[c];
             __syncwarp();
-            float* row = p.grad_arena + (size_t)s_id[warp][j] * p.grad_stride;
+            float* row = p.grad_arena + (size_t)s_id[lw][j] * p.grad_stride;
             const int n_live = kGradFeature + p.S;  // padding channels carry no gradient
 #pragma unroll
             for (int pass = 0; pass < (kTwoPass ? 2 : 1); ++pass) {
@@ -280,28 +286,47 @@ render_bwd_kernel(const RenderBwdParams p) {
 
 }  // namespace
 
-int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream) {
-    const dim3 grid(p.grid_x, p.grid_y);
-    switch (p.cf_stride / 4) {
-#define MRGS_CASE(NQ)                                                                              \
-    case NQ: {                                                                                     \
-        static bool configured = false;                                                            \
-        if (!configured) {                                                                         \
-            cudaFuncSetAttribute(render_bwd_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                 bwd_smem_bytes<NQ>());                                            \
-            configured = true;                                                                     \
-        }                                                                                          \
-        render_bwd_kernel<NQ><<<grid, kTilePixels, bwd_smem_bytes<NQ>(), stream>>>(p);             \
-        break;                                                                                     \
+namespace {
+
+template <int NQ, int WPC, int MINB>
+void launch_variant(const RenderBwdParams& p, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(render_bwd_kernel<NQ, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             bwd_smem_bytes<NQ, WPC>());
+        configured = true;
     }
-        MRGS_CASE(1)
-        MRGS_CASE(2)
-        MRGS_CASE(3)
-        MRGS_CASE(4)
-        MRGS_CASE(5)
-        MRGS_CASE(6)
-        MRGS_CASE(7)
-#undef MRGS_CASE
+    const dim3 grid(p.grid_x, p.grid_y, kWarpsPerTile / WPC);
+    render_bwd_kernel<NQ, WPC, MINB><<<grid, WPC * 32, bwd_smem_bytes<NQ, WPC>(), stream>>>(p);
+}
+
+// MRGS_BWD_SPLIT=82 selects the unsplit launch (8 warps per CTA, 2 CTAs per SM) of the S <= 9 kernel for A/B
+// measurements. Measured at C3 (profiles/r01_v7_summary.md): 8x2 1.029 ms, 4x4 0.997, 4x5 0.952, 1x20 0.952,
+// 2x10 0.995, 4x6 (80 registers, spills) 1.058.
+bool bwd_unsplit() {
+    static const bool v = [] {
+        const char* e = getenv("MRGS_BWD_SPLIT");
+        return e != nullptr && atoi(e) == 82;
+    }();
+    return v;
+}
+
+}  // namespace
+
+int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream) {
+    switch (p.cf_stride / 4) {
+        case 1: launch_variant<1, 4, 5>(p, stream); break;
+        case 2: launch_variant<2, 4, 5>(p, stream); break;
+        case 3:
+            if (bwd_unsplit())
+                launch_variant<3, 8, 2>(p, stream);
+            else
+                launch_variant<3, 4, 5>(p, stream);
+            break;
+        case 4: launch_variant<4, 4, 2>(p, stream); break;
+        case 5: launch_variant<5, 4, 2>(p, stream); break;
+        case 6: launch_variant<6, 4, 2>(p, stream); break;
+        case 7: launch_variant<7, 4, 2>(p, stream); break;
         default:
             set_error("render_bwd: unsupported feature count S=%d (max %d)", p.S, MRGS_MAX_FEATURES);
             return MRGS_ERR_UNSUPPORTED;
