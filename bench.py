@@ -176,6 +176,8 @@ class OursStep:
         self.arena = GradArena.create(WORKLOAD["P"], dev)
         self.arena.bind(self.leaves)
         self.sink = self.arena.views if self.name == "ours" else None
+        # texel gradients of the mip chain: summed over the step's views in one persistent buffer (shading.py)
+        self.level_sink = self.env.enable_level_grad_sink() if self.name == "ours" else None
         self.last = {}
 
     def zero_grads(self):
@@ -231,8 +233,10 @@ class OursStep:
         if e2e:
             self.copy_stream.synchronize()
             total = float(sum(float(self.loss_host[v]) + float(self.img_host[v][0, 0, 0]) for v in range(V)))
-        if self.world > 1:
-            self.arena.allreduce()         # autograd accumulated in place: no flattening copy
+        if self.world > 1:                 # autograd accumulated in place: no flattening copy
+            self.arena.allreduce(extra=(self.level_sink,) if self.level_sink is not None else ())
+        if self.level_sink is not None:
+            self.env.flush_level_grads()   # the (all-reduced) chain gradient reaches the levels' .grad once per step
         return total if e2e else None
 
     # ---- end-to-end plumbing: pinned host buffers, one copy stream, double-buffered device inputs ----------

@@ -101,11 +101,15 @@ class GradArena:
         self.stats[:, 1].add_(vis.to(torch.float32))
         torch.maximum(self.max_radii, torch.where(vis, radii, torch.zeros_like(radii)), out=self.max_radii)
 
-    def allreduce(self, group=None):
-        """ONE sum-allreduce for gradients + statistics and one max-allreduce for the radii."""
+    def allreduce(self, group=None, extra=()):
+        """ONE sum-allreduce for gradients + statistics and one max-allreduce for the radii. `extra`: further
+        buffers to sum across ranks in the same breath (the environment map's texel-gradient sink, 33 MB at
+        6 x 512^2: EnvLight.level_grad_sink)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        for t in extra:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
 
 

@@ -77,7 +77,8 @@ class _ShadeSurfel(torch.autograd.Function):
     def forward(ctx, base_color, features, allmap, bg, cfg, *levels):
         lib = _lib.load()
         dev = base_color.device
-        M, Q, min_r, max_r, srgb = cfg
+        M, Q, min_r, max_r, srgb = cfg[:5]
+        ctx.set_materialize_grads(False)   # outputs nobody differentiates arrive as None, not as zero-filled maps
         base_color, features, allmap = base_color.contiguous(), features.contiguous(), allmap.contiguous()
         levels = tuple(l.contiguous() for l in levels)
         if features.shape[0] < 5:
@@ -105,7 +106,8 @@ class _ShadeSurfel(torch.autograd.Function):
         lib = _lib.load()
         base_color, features, allmap, bg, *levels = ctx.saved_tensors
         dev = base_color.device
-        M, Q, min_r, max_r, srgb = ctx.cfg
+        M, Q, min_r, max_r, srgb = ctx.cfg[:5]
+        sink = ctx.cfg[5] if len(ctx.cfg) > 5 else None     # EnvLight.level_grad_sink: [texels, 4] accumulation buffer
         H, W = base_color.shape[1], base_color.shape[2]
         a = _chain_args(levels, min_r, max_r)
         a.width, a.height, a.srgb = W, H, int(bool(srgb))
@@ -114,21 +116,30 @@ class _ShadeSurfel(torch.autograd.Function):
         lut = fg_lut(dev)
         a.background, a.base_color, a.features, a.allmap, a.lut = (
             bg.data_ptr(), base_color.data_ptr(), features.data_ptr(), allmap.data_ptr(), lut.data_ptr())
-        keep = [g.contiguous() for g in (g_final, g_spec, g_normal, g_diffuse)]
-        a.dL_dfinal, a.dL_dspecular, a.dL_dnormal, a.dL_ddiffuse = (g.data_ptr() for g in keep)
+        keep = [None if g is None else g.contiguous() for g in (g_final, g_spec, g_normal, g_diffuse)]
+        a.dL_dfinal, a.dL_dspecular, a.dL_dnormal, a.dL_ddiffuse = (None if g is None else g.data_ptr() for g in keep)
         d_base = torch.empty_like(base_color)
         d_feat = torch.zeros_like(features) if features.shape[0] > 5 else torch.empty_like(features)
         d_allmap = torch.zeros_like(allmap)
         # one flat [texels, 4] accumulation buffer for the whole chain (16-byte texels for vector atomics)
         counts = [l.shape[0] * l.shape[1] * l.shape[2] for l in levels]
-        flat4 = torch.zeros((sum(counts), 4), dtype=torch.float32, device=dev)
+        need_levels = any(ctx.needs_input_grad[5:])
+        if sink is not None:
+            if tuple(sink.shape) != (sum(counts), 4) or sink.device != dev or sink.dtype != torch.float32:
+                raise RuntimeError(f"level_grad_sink must be a float32 [{sum(counts)}, 4] tensor on {dev}")
+            flat4 = sink
+        else:
+            flat4 = torch.zeros((sum(counts), 4), dtype=torch.float32, device=dev) if need_levels else None
         a.dL_dbase_color, a.dL_dfeatures, a.dL_dallmap = d_base.data_ptr(), d_feat.data_ptr(), d_allmap.data_ptr()
         off = 0
         for i, n in enumerate(counts):
-            a.dL_dlevels[i] = flat4.data_ptr() + off * 16
+            if flat4 is not None:
+                a.dL_dlevels[i] = flat4.data_ptr() + off * 16
             off += n
         with torch.cuda.device(dev):
             _lib.check(lib.mrgs_shade_backward(C.byref(a), _stream(dev)), "mrgs_shade_backward")
+        if sink is not None or flat4 is None:    # the sink owns the texel gradients (EnvLight.flush_level_grads)
+            return (d_base, d_feat, d_allmap, None, None, *([None] * len(levels)))
         flat3 = flat4[:, :3].contiguous()
         d_levels, off = [], 0
         for l, n in zip(levels, counts):
@@ -196,7 +207,8 @@ def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, 
     """Everything render_surfel does after the rasterizer call except depth_to_normal
     (gaussian_renderer/__init__.py:372-469). HWK = (H, W, K) and R (c2w rotation) come from the
     camera exactly as the reference passes `viewpoint_camera.HWK / .R`."""
-    cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb)
+    cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb,
+           getattr(envmap, "level_grad_sink", None))
     final, specular, direct, normal_w, diffuse = _ShadeSurfel.apply(
         rendered_image, rendered_features, allmap, bg_color, cfg, *envmap.specular)
     return {
@@ -324,6 +336,35 @@ class EnvLight(torch.nn.Module):
     def set_chain(self, levels):
         """Install an externally built mip chain (tests / benchmarks)."""
         self.specular = list(levels)
+
+    level_grad_sink = None
+
+    def enable_level_grad_sink(self):
+        """Multi-view steps: let the shading backward ADD the texel gradients of every view into ONE persistent
+        [texels, 4] buffer instead of returning them through autograd (per view that costs a zero-fill of the buffer, a
+        strided copy to [.,3] and one accumulation pass per level). Call flush_level_grads() once per step: it feeds the
+        summed gradients into the mip chain's autograd graph (or the levels' .grad when they are leaves) and clears the
+        buffer. Gradients are linear in the upstream gradient, so the result equals per-view accumulation."""
+        n = sum(l.shape[0] * l.shape[1] * l.shape[2] for l in self.specular)
+        dev = self.specular[0].device
+        if self.level_grad_sink is None or self.level_grad_sink.shape[0] != n or self.level_grad_sink.device != dev:
+            self.level_grad_sink = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+        return self.level_grad_sink
+
+    def flush_level_grads(self):
+        sink = self.level_grad_sink
+        if sink is None:
+            return
+        flat3 = sink[:, :3].contiguous()
+        grads, off = [], 0
+        for l in self.specular:
+            n = l.shape[0] * l.shape[1] * l.shape[2]
+            grads.append(flat3[off:off + n].view(l.shape))
+            off += n
+        live = [(l, g) for l, g in zip(self.specular, grads) if l.requires_grad]
+        if live:
+            torch.autograd.backward([l for l, _ in live], grad_tensors=[g for _, g in live])
+        sink.zero_()
 
     def get_mip(self, roughness):
         n = len(self.specular)

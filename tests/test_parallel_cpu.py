@@ -66,7 +66,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(420)
 def test_view_sharded_step_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -74,7 +74,7 @@ def test_view_sharded_step_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=100) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0
@@ -145,7 +145,7 @@ def _densify_worker(rank, world, port, q):
             dist.destroy_process_group()
 
 
-@pytest.mark.timeout(120)
+@pytest.mark.timeout(420)
 def test_ranks_densify_to_the_same_cloud_world2_gloo():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
@@ -153,7 +153,7 @@ def test_ranks_densify_to_the_same_cloud_world2_gloo():
     procs = [ctx.Process(target=_densify_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=100) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
         p.join(timeout=30)
         assert p.exitcode == 0

@@ -195,3 +195,42 @@ def test_envlight_query_keeps_leading_shape_and_reaches_the_base_cubemap():
     assert out.shape == (4, 5, 6, 3)
     out.sum().backward()
     assert env.base.grad is not None and env.base.grad.abs().sum().item() > 0
+
+
+def test_level_grad_sink_equals_per_view_autograd_accumulation():
+    """EnvLight.enable_level_grad_sink(): the texel gradients of several views summed in the persistent buffer and
+    flushed once equal what autograd accumulates view by view; outputs nobody differentiates cost no zero maps."""
+    from materialrefgs_b200.shading import shade_surfel
+    H, W = 96, 128
+    levels = so.synthetic_chain(64, 16, device=DEV)
+    bg = torch.tensor([0.1, 0.2, 0.3], device=DEV)
+    views = []
+    for v in (1, 3, 5):
+        base, feats, allmap = so.synthetic_gbuffer(H, W, device=DEV, seed=v)
+        views.append((synthetic.orbit_camera(v, 8, W, H), base, feats, allmap,
+                      torch.randn(3, H, W, generator=torch.Generator().manual_seed(v)).to(DEV)))
+
+    def run(use_sink):
+        lv = [l.clone().requires_grad_(True) for l in levels]
+        env = _env(lv)
+        if use_sink:
+            env.enable_level_grad_sink()
+        feat_grads = []
+        for cam, base, feats, allmap, w in views:
+            f = feats.clone().requires_grad_(True)
+            out = shade_surfel(env, base, f, allmap, cam.HWK, cam.R, bg)
+            (out["render"] * w).sum().backward()          # only ONE of the five outputs carries a gradient
+            feat_grads.append(f.grad)
+            if use_sink:
+                assert all(l.grad is None for l in lv)     # nothing reaches the levels before the flush
+        if use_sink:
+            env.flush_level_grads()
+            assert not env.level_grad_sink.any()
+        return [l.grad for l in lv], feat_grads
+
+    a_lv, a_f = run(True)
+    b_lv, b_f = run(False)
+    for a, b in zip(a_lv, b_lv):
+        assert _rel(a, b) <= 1e-5
+    for a, b in zip(a_f, b_f):
+        assert torch.equal(a, b)
