@@ -526,14 +526,14 @@ def main():
     line["config"]["R"] = int(R)
     line["gpu_launches"] = launches
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-    # (profiles/r01_v4_summary.md); only valid for the default C3 workload
-    traffic = {"render_bwd": 115.9e6 + 9.0e6, "render_fwd": 43.5e6 + 17.9e6}.get(dom) if WORKLOAD["P"] == 1_000_000 else None
+    # (profiles/r01_v7_summary.md); only valid for the default C3 workload
+    traffic = {"render_bwd": 103.9e6 + 6.0e6, "render_fwd": 32.2e6 + 13.6e6}.get(dom) if WORKLOAD["P"] == 1_000_000 else None
     line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
                         "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": stage_ms[dom],
-                        "note": "tile-blend kernels are instruction-issue bound (ncu: issue slots 64-78 % busy, DRAM ~1 % of peak), "
+                        "note": "tile-blend kernels are instruction-issue bound (ncu: issue slots 72-78 % busy, DRAM ~1.5 % of peak), "
                                 "not HBM bound; DRAM traffic is ~10x below the algorithmic bytes because neighbouring tiles share "
-                                "list entries in L2; see profiles/r01_v4_summary.md"}
+                                "list entries in L2; see profiles/r01_v7_summary.md"}
     frame_bytes = ab["frame_raster"] + ab["frame_shade"]
     ms_per_frame = ms_per_step / VIEWS_PER_RANK
     line["frame_roofline"] = {"algorithmic_bytes_per_frame": frame_bytes,
