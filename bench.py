@@ -491,7 +491,7 @@ def main():
         "config": {"workload": "C3: 1M random-init surfels (trained-like opacity), 800x800, S=8 material channels, "
                                "SH degree 3, rasterize + fused deferred PBR shading (6x512^2 cubemap, 6 mips), fwd+bwd",
                    "P": P, "Pv": Pv, "N": N, "S": WORKLOAD["S"], "views_per_step": world_eff * VIEWS_PER_RANK, "views_per_rank": VIEWS_PER_RANK,
-                   "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the P*68-float gradient+statistics arena" if world_eff > 1 else ""),
+                   "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the P*68-float gradient+statistics arena + 1 of the 33 MB environment-map gradient sink" if world_eff > 1 else ""),
                    "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient arenas) exceeds the 126 MB L2"},
         "e2e": {"value": world_eff * VIEWS_PER_RANK * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
                 "d2h_bytes_per_step": stepper.d2h_bytes(),
