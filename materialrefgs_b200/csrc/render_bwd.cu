@@ -25,6 +25,8 @@ namespace {
 
 constexpr unsigned kFull = 0xffffffffu;
 
+__device__ __forceinline__ void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+
 constexpr int kRedStride = 36;  // floats per value row: 32 lanes + 4 pad keeps LDS.128 conflict-free
 
 template <int NQ, int WPC>
@@ -35,8 +37,8 @@ constexpr int bwd_smem_bytes() {
 }
 
 // WPC warps per CTA: the warps of a tile never synchronise with each other, so a tile can be split over 8 / WPC CTAs
-// (blockIdx.z) — the register file then holds a non-integer number of TILES per SM (e.g. 5 CTAs of 4 warps at <= 102
-// registers = 20 warps instead of 2 CTAs of 8 = 16).
+// (blockIdx.z) — the register file then holds a non-integer number of TILES per SM (6 CTAs of 4 warps at 80
+// registers = 24 warps instead of 2 CTAs of 8 = 16), and a finished warp frees its slot without waiting for its tile.
 template <int NQ, int WPC, int MINB>
 __global__ void __launch_bounds__(WPC * 32, MINB)
 render_bwd_kernel(const RenderBwdParams p) {
@@ -124,23 +126,27 @@ render_bwd_kernel(const RenderBwdParams p) {
 
     // back-to-front in steps of 32 list entries; lane l of a step holds entry hi-1-l, so walking the
     // survivor mask from bit 0 upwards visits entries in descending order
+    // software pipeline: the NEXT step's id is loaded and its 32-byte bound (box + diagonal slabs, one sector) is
+    // pulled into L1 with a prefetch while the current survivors are processed — a prefetch holds no registers,
+    // where keeping the two float4 in flight cost 8 per thread across the whole gradient math
     uint32_t id_next = 0;
-    float4 bb_next = make_float4(0.f, 0.f, -1.f, -1.f), bd_next = bb_next;
     if (warp_last - 1 - lane >= 0) {
         id_next = list[warp_last - 1 - lane];
-        bb_next = p.bbox[2 * id_next];
-        bd_next = p.bbox[2 * id_next + 1];
+        prefetch_l1(p.bbox + 2 * (size_t)id_next);
     }
 
     for (int hi = warp_last; hi > 0; hi -= 32) {
         const uint32_t id = id_next;
-        const float4 bb = bb_next, bd = bd_next;
         const int e_mine = hi - 1 - lane;
         const int e_next = e_mine - 32;
+        float4 bb = make_float4(0.f, 0.f, -1.f, -1.f), bd = bb;
+        if (e_mine >= 0) {
+            bb = p.bbox[2 * (size_t)id];
+            bd = p.bbox[2 * (size_t)id + 1];
+        }
         if (e_next >= 0) {
             id_next = list[e_next];
-            bb_next = p.bbox[2 * id_next];
-            bd_next = p.bbox[2 * id_next + 1];
+            prefetch_l1(p.bbox + 2 * (size_t)id_next);
         }
         const bool keep = (e_mine >= 0) && !(bb.x > bx1 || bb.z < bx0 || bb.y > by1 || bb.w < by0) &&
                           !(bd.x > bu1 || bd.z < bu0 || bd.y > bv1 || bd.w < bv0);
@@ -169,9 +175,13 @@ render_bwd_kernel(const RenderBwdParams p) {
             const bool valid = (e < last_contributor) && ray_splat(g0, g1, g2, g3.w, pxf, pyf, h);
             if (!__any_sync(kFull, valid)) continue;
 
-            float v[NV];
+            // v: the 12 geometric values that exist only for pixels the instance touches. The colour/feature and
+            // normal gradients are all w * (a per-pixel constant): only w leaves the branch (0 for untouched pixels)
+            // and the products are formed at the store, so they never occupy registers across the gradient math.
+            float v[kGradNormal];
 #pragma unroll
-            for (int c = 0; c < NV; ++c) v[c] = 0.0f;
+            for (int c = 0; c < kGradNormal; ++c) v[c] = 0.0f;
+            float w_out = 0.0f;
 
             if (valid) {
                 const float alpha = h.alpha, G = h.G;
@@ -181,19 +191,13 @@ render_bwd_kernel(const RenderBwdParams p) {
                 const float w = alpha * T;
                 float q;
                 {
-                    // two channels per instruction (Blackwell packed fp32: fma.rn.f32x2 / mul.rn.f32x2)
-                    const float2 w2 = make_float2(w, w);
+                    // two channels per instruction (Blackwell packed fp32: fma.rn.f32x2)
                     float2 dot2 = make_float2(0.0f, 0.0f);
 #pragma unroll
                     for (int k = 0; k < NQ; ++k) {
                         const float4 cv = s_cf[lw][k][j];
                         dot2 = __ffma2_rn(make_float2(cv.x, cv.y), dL_dpix[2 * k], dot2);
                         dot2 = __ffma2_rn(make_float2(cv.z, cv.w), dL_dpix[2 * k + 1], dot2);
-                        const float2 ga = __fmul2_rn(w2, dL_dpix[2 * k]), gb = __fmul2_rn(w2, dL_dpix[2 * k + 1]);
-                        v[kGradColor + 4 * k + 0] = ga.x;
-                        v[kGradColor + 4 * k + 1] = ga.y;
-                        v[kGradColor + 4 * k + 2] = gb.x;
-                        v[kGradColor + 4 * k + 3] = gb.y;
                     }
                     q = dot2.x + dot2.y;
                 }
@@ -211,9 +215,7 @@ render_bwd_kernel(const RenderBwdParams p) {
 
                 // depth, alpha ("colour" 1) and normal are blended channels like the colours
                 q += c_d * dL_ddepth + dL_daccum + g3.x * dL_dn0 + g3.y * dL_dn1 + g3.z * dL_dn2;
-                v[kGradNormal + 0] = w * dL_dn0;
-                v[kGradNormal + 1] = w * dL_dn1;
-                v[kGradNormal + 2] = w * dL_dn2;
+                w_out = w;
 
                 float dL_dalpha = T * (q + dist_term) - inv_1ma * behind;
                 behind += w * q;
@@ -259,7 +261,19 @@ render_bwd_kernel(const RenderBwdParams p) {
             // transpose through shared memory: lane c sums value c over the 32 pixels (8 LDS.128 + 31 FADD)
             // and the warp leaves ONE coalesced red.global.add per arena row
 #pragma unroll
-            for (int c = 0; c < NV; ++c) s_red[c * kRedStride + lane] = v[c];
+            for (int c = 0; c < kGradNormal; ++c) s_red[c * kRedStride + lane] = v[c];
+            s_red[(kGradNormal + 0) * kRedStride + lane] = w_out * dL_dn0;
+            s_red[(kGradNormal + 1) * kRedStride + lane] = w_out * dL_dn1;
+            s_red[(kGradNormal + 2) * kRedStride + lane] = w_out * dL_dn2;
+            {
+                const float2 w2 = make_float2(w_out, w_out);
+#pragma unroll
+                for (int k = 0; k < NC / 2; ++k) {
+                    const float2 g = __fmul2_rn(w2, dL_dpix[k]);   // mul.rn.f32x2
+                    s_red[(kGradColor + 2 * k + 0) * kRedStride + lane] = g.x;
+                    s_red[(kGradColor + 2 * k + 1) * kRedStride + lane] = g.y;
+                }
+            }
             __syncwarp();
             float* row = p.grad_arena + (size_t)s_id[lw][j] * p.grad_stride;
             const int n_live = kGradFeature + p.S;  // padding channels carry no gradient
@@ -301,8 +315,10 @@ void launch_variant(const RenderBwdParams& p, cudaStream_t stream) {
 }
 
 // MRGS_BWD_SPLIT=82 selects the unsplit launch (8 warps per CTA, 2 CTAs per SM) of the S <= 9 kernel for A/B
-// measurements. Measured at C3 (profiles/r01_v7_summary.md): 8x2 1.029 ms, 4x4 0.997, 4x5 0.952, 1x20 0.952,
-// 2x10 0.995, 4x6 (80 registers, spills) 1.058.
+// measurements. Measured at C3 (profiles/r01_v7_summary.md), first with 127 registers of natural demand: 8x2 1.029 ms,
+// 4x4 0.997, 4x5 (96 regs) 0.952, 1x20 0.952, 2x10 0.995, 4x6 (80 regs, 108 B spill) 1.058; then with the register diet
+// (products formed at the store, L1 prefetch of the next bounds: 106 registers of natural demand): 4x5 0.888,
+// 4x6 (80 regs, 4 B spill) 0.872, 4x7 (72 regs, 28 B spill) 0.945.
 bool bwd_unsplit() {
     static const bool v = [] {
         const char* e = getenv("MRGS_BWD_SPLIT");
@@ -315,13 +331,13 @@ bool bwd_unsplit() {
 
 int launch_render_bwd(const RenderBwdParams& p, cudaStream_t stream) {
     switch (p.cf_stride / 4) {
-        case 1: launch_variant<1, 4, 5>(p, stream); break;
-        case 2: launch_variant<2, 4, 5>(p, stream); break;
+        case 1: launch_variant<1, 4, 6>(p, stream); break;
+        case 2: launch_variant<2, 4, 6>(p, stream); break;
         case 3:
             if (bwd_unsplit())
                 launch_variant<3, 8, 2>(p, stream);
             else
-                launch_variant<3, 4, 5>(p, stream);
+                launch_variant<3, 4, 6>(p, stream);
             break;
         case 4: launch_variant<4, 4, 2>(p, stream); break;
         case 5: launch_variant<5, 4, 2>(p, stream); break;
