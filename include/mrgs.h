@@ -299,6 +299,34 @@ MRGS_API int mrgs_envlight_query_backward(const MrgsShadeArgs* chain, int64_t n,
                                           const float* roughness, const float* dL_dout, float* dL_ddirs,
                                           float* dL_droughness, void* stream);
 
+/* Per-SURFEL split-sum colours of the volume-rendering stage: get_full_color_volume / get_full_color_volume_indirect
+ * (utils/refl_utils.py:426-490, visibility = 1) as one kernel pair. For every surfel i:
+ *   w_o = safe_normalize(campos - xyz); NdotV = w_o . n; rr = safe_normalize(2 n NdotV - w_o)
+ *   diffuse      = sigmoid(cube fetch of diffuse_map in direction n) * (1 - refl) * albedo
+ *   direct_light = sigmoid(cube fetch of the chain in direction rr at get_mip(roughness))
+ *   specular     = direct_light * ((0.04 (1 - refl) + albedo refl) * fg[0] + fg[1])
+ * `fg` (device [2]) is ONE pair for all surfels: the reference indexes `fg[0]` on the [N,2] LUT result, i.e. the FIRST
+ * surfel's pair (:445, :481) — the caller evaluates it; the backward returns its gradient as the sum dL_dfg [2]
+ * (ACCUMULATED, zero it first). `chain` supplies levels / num_levels / base_res / min,max roughness / dL_dlevels
+ * (float4 texels, accumulated). dL_ddiffuse_map is float4 per texel, accumulated. Outputs [P,3] (direct_light may be
+ * NULL); backward inputs NULL = zero; backward outputs are fully written when non-NULL. */
+typedef struct MrgsSurfelShadeArgs {
+    int32_t P;
+    int32_t diffuse_res;
+    MrgsShadeArgs chain;
+    const float* diffuse_map;      /* [6,diffuse_res,diffuse_res,3] */
+    const float* campos;           /* device [3] */
+    const float* fg;               /* device [2] */
+    const float *xyz, *normals, *albedo, *refl_strength, *roughness;
+    float *diffuse, *specular, *direct_light;
+    const float *dL_ddiffuse, *dL_dspecular, *dL_ddirect;
+    float *dL_dxyz, *dL_dnormals, *dL_dalbedo, *dL_drefl_strength, *dL_droughness;
+    float* dL_ddiffuse_map;
+    float* dL_dfg;
+} MrgsSurfelShadeArgs;
+MRGS_API int mrgs_surfel_shade_forward(const MrgsSurfelShadeArgs* args, void* stream);
+MRGS_API int mrgs_surfel_shade_backward(const MrgsSurfelShadeArgs* args, void* stream);
+
 /* ---- pseudo surface depth + depth_to_normal ------------------------------------------------------
  * compute_2dgs_normal_and_regularizations (gaussian_renderer/__init__.py:50-78) + depth_to_normal
  * (utils/point_utils.py:9-37) in one launch:

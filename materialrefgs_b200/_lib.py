@@ -93,6 +93,14 @@ class ShadeArgs(C.Structure):
     ]
 
 
+class SurfelShadeArgs(C.Structure):
+    """MrgsSurfelShadeArgs (include/mrgs.h)."""
+    _fields_ = [("P", C.c_int32), ("diffuse_res", C.c_int32), ("chain", ShadeArgs)] + [(n, _fp) for n in (
+        "diffuse_map", "campos", "fg", "xyz", "normals", "albedo", "refl_strength", "roughness", "diffuse", "specular",
+        "direct_light", "dL_ddiffuse", "dL_dspecular", "dL_ddirect", "dL_dxyz", "dL_dnormals", "dL_dalbedo",
+        "dL_drefl_strength", "dL_droughness", "dL_ddiffuse_map", "dL_dfg")]
+
+
 # every symbol include/mrgs.h declares: name -> (restype, argtypes)
 class SurfelFeatureArgs(C.Structure):
     _fields_ = [("P", C.c_int32), ("campos", _fp)] + [(n, _fp) for n in (
@@ -132,6 +140,8 @@ SYMBOLS = {
     "mrgs_shade_forward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_shade_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_envlight_query": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, C.c_void_p]),
+    "mrgs_surfel_shade_forward": (C.c_int, [C.POINTER(SurfelShadeArgs), C.c_void_p]),
+    "mrgs_surfel_shade_backward": (C.c_int, [C.POINTER(SurfelShadeArgs), C.c_void_p]),
     "mrgs_envlight_query_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, _fp, _fp, C.c_void_p]),
     "mrgs_depth_normal_forward": (C.c_int, [C.c_int32, C.c_int32, C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_float),
                                             _fp, _fp, _fp, C.c_void_p]),

@@ -640,6 +640,30 @@ int mrgs_envlight_query_backward(const MrgsShadeArgs* chain, int64_t n, const fl
     return MRGS_OK;
 }
 
+int mrgs_surfel_shade_forward(const MrgsSurfelShadeArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_FWD, stream, 1);
+        st = launch_surfel_shade(a, false, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("surfel_shade_fwd", stream, false);
+    return MRGS_OK;
+}
+
+int mrgs_surfel_shade_backward(const MrgsSurfelShadeArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st;
+    {
+        StageScope sc(MRGS_STAGE_SHADE_BWD, stream, 1);
+        st = launch_surfel_shade(a, true, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("surfel_shade_bwd", stream, false);
+    return MRGS_OK;
+}
+
 int mrgs_depth_normal_forward(int32_t width, int32_t height, float depth_ratio, const float* host_ray_matrix,
                               const float* host_origin, const float* allmap, float* surf_depth, float* surf_normal,
                               void* stream_) {

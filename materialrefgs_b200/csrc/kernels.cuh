@@ -131,6 +131,7 @@ int launch_img_grad_weight(const float* img, int C, int H, int W, float* out, vo
 int launch_surfel_features(const MrgsSurfelFeatureArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                           float* out, cudaStream_t stream);
+int launch_surfel_shade(const MrgsSurfelShadeArgs* a, bool backward, cudaStream_t stream);
 int launch_envlight_query_bwd(const MrgsShadeArgs* a, long long n, const float* dirs, const float* roughness,
                               const float* dL_dout, float* dL_ddirs, float* dL_droughness, cudaStream_t stream);
 

@@ -396,6 +396,186 @@ envlight_query_bwd_kernel(const MrgsShadeArgs p, long long n, const float* __res
     }
 }
 
+// ---- per-surfel split-sum colours of the volume-rendering stage ---------------------------------------------------
+// get_full_color_volume / get_full_color_volume_indirect (utils/refl_utils.py:426-490, visibility = 1) as ONE kernel
+// pair instead of ~25 eager P-sized torch kernels around two dr.texture calls:
+//   w_o = safe_normalize(campos - xyz); NdotV = w_o . n; rr = safe_normalize(2 n NdotV - w_o)
+//   diffuse  = sigmoid(tex(diffuse map, n)) * (1 - refl) * albedo
+//   direct   = sigmoid(tex(specular chain, rr, roughness))
+//   specular = direct * ((0.04 (1 - refl) + albedo refl) * fg.x + fg.y)
+// `fg` is ONE pair for all surfels: the reference indexes fg[0] on the [N,2] LUT result (:445, :481), i.e. the first
+// surfel's pair; the host mirror evaluates it and gets its gradient back as the 2-float sum `dL_dfg`.
+struct SurfelShade {
+    F3 n, wo, r, rr, albedo, dl, Ld, sw;
+    float rs, ro, ndv, rl, vl;
+    MipLevel mip;
+    FaceUV fn, fr;
+    Bilinear bn, b0, b1;
+};
+
+template <bool GRAD>
+__device__ __forceinline__ void shade_one_surfel(const MrgsSurfelShadeArgs& p, long long i, float fgx, float fgy,
+                                                 SurfelShade& s) {
+    const F3 x = {p.xyz[3 * i], p.xyz[3 * i + 1], p.xyz[3 * i + 2]};
+    s.n = {p.normals[3 * i], p.normals[3 * i + 1], p.normals[3 * i + 2]};
+    s.albedo = {p.albedo[3 * i], p.albedo[3 * i + 1], p.albedo[3 * i + 2]};
+    s.rs = p.refl_strength[i];
+    s.ro = p.roughness[i];
+    const F3 v = {p.campos[0] - x.x, p.campos[1] - x.y, p.campos[2] - x.z};
+    s.vl = fmaxf(sqrtf(dot(v, v)), 1e-20f);
+    s.wo = (1.0f / s.vl) * v;
+    s.ndv = dot(s.wo, s.n);
+    s.r = (2.0f * s.ndv) * s.n - s.wo;
+    s.rl = fmaxf(sqrtf(dot(s.r, s.r)), 1e-20f);
+    s.rr = (1.0f / s.rl) * s.r;
+    // diffuse: plain bilinear fetch of the cosine-convolved map in the direction of the normal
+    s.fn = dir_to_face(s.n);
+    cube_bilinear<GRAD>(p.diffuse_map, p.diffuse_res, s.fn.face, s.fn.u, s.fn.v, s.bn);
+    s.dl = {sigmoidf(s.bn.val.x), sigmoidf(s.bn.val.y), sigmoidf(s.bn.val.z)};
+    // specular: trilinear fetch of the GGX chain in the reflected direction
+    s.mip = rough_to_level(s.ro, p.chain.min_roughness, p.chain.max_roughness, p.chain.num_levels);
+    s.fr = dir_to_face(s.rr);
+    cube_bilinear<GRAD>(p.chain.levels[s.mip.l0], p.chain.base_res >> s.mip.l0, s.fr.face, s.fr.u, s.fr.v, s.b0);
+    F3 t = s.b0.val;
+    if (s.mip.l1 != s.mip.l0) {
+        cube_bilinear<GRAD>(p.chain.levels[s.mip.l1], p.chain.base_res >> s.mip.l1, s.fr.face, s.fr.u, s.fr.v, s.b1);
+        t = (1.0f - s.mip.f) * s.b0.val + s.mip.f * s.b1.val;
+    }
+    s.Ld = {sigmoidf(t.x), sigmoidf(t.y), sigmoidf(t.z)};
+    const float k0 = 0.04f * (1.0f - s.rs);
+    s.sw = {(k0 + s.albedo.x * s.rs) * fgx + fgy, (k0 + s.albedo.y * s.rs) * fgx + fgy,
+            (k0 + s.albedo.z * s.rs) * fgx + fgy};
+}
+
+__device__ __forceinline__ void store3i(float* out, long long i, F3 v) {
+    if (out == nullptr) return;
+    out[3 * i] = v.x;
+    out[3 * i + 1] = v.y;
+    out[3 * i + 2] = v.z;
+}
+__device__ __forceinline__ F3 load3i(const float* in, long long i) {
+    if (in == nullptr) return {0.f, 0.f, 0.f};
+    return {in[3 * i], in[3 * i + 1], in[3 * i + 2]};
+}
+
+__global__ void __launch_bounds__(256) surfel_shade_fwd_kernel(const MrgsSurfelShadeArgs p) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.P) return;
+    SurfelShade s;
+    shade_one_surfel<false>(p, i, p.fg[0], p.fg[1], s);
+    const float om = 1.0f - s.rs;
+    store3i(p.diffuse, i, {s.dl.x * om * s.albedo.x, s.dl.y * om * s.albedo.y, s.dl.z * om * s.albedo.z});
+    store3i(p.specular, i, {s.Ld.x * s.sw.x, s.Ld.y * s.sw.y, s.Ld.z * s.sw.z});
+    store3i(p.direct_light, i, s.Ld);
+}
+
+// The 6 x 16^2 diffuse map is sampled by every surfel: its texel gradients are summed in shared memory and flushed
+// once per CTA (grid-stride loop over few, fat CTAs), like envlight_query_bwd_kernel<true>.
+template <bool SMALL>
+__global__ void __launch_bounds__(256) surfel_shade_bwd_kernel(const MrgsSurfelShadeArgs p) {
+    __shared__ float s_acc[SMALL ? kSmallTexels * 3 : 1];
+    __shared__ float s_fg[2][8];
+    const int texels_d = 6 * p.diffuse_res * p.diffuse_res;
+    if (SMALL) {
+        for (int k = threadIdx.x; k < texels_d * 3; k += blockDim.x) s_acc[k] = 0.f;
+        __syncthreads();
+    }
+    const float fgx = p.fg[0], fgy = p.fg[1];
+    float acc_fgx = 0.f, acc_fgy = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < p.P; i += (long long)gridDim.x * blockDim.x) {
+        SurfelShade s;
+        shade_one_surfel<true>(p, i, fgx, fgy, s);
+        const F3 g_diff = load3i(p.dL_ddiffuse, i), g_spec = load3i(p.dL_dspecular, i), g_dir = load3i(p.dL_ddirect, i);
+        const float om = 1.0f - s.rs;
+        // diffuse = dl * (1 - rs) * albedo
+        const F3 g_dl = {g_diff.x * om * s.albedo.x, g_diff.y * om * s.albedo.y, g_diff.z * om * s.albedo.z};
+        float g_rs = -(g_diff.x * s.dl.x * s.albedo.x + g_diff.y * s.dl.y * s.albedo.y + g_diff.z * s.dl.z * s.albedo.z);
+        F3 g_albedo = {g_diff.x * s.dl.x * om, g_diff.y * s.dl.y * om, g_diff.z * s.dl.z * om};
+        // specular = Ld * sw, direct = Ld
+        const F3 g_Ld = {g_spec.x * s.sw.x + g_dir.x, g_spec.y * s.sw.y + g_dir.y, g_spec.z * s.sw.z + g_dir.z};
+        const F3 g_sw = {g_spec.x * s.Ld.x, g_spec.y * s.Ld.y, g_spec.z * s.Ld.z};
+        g_rs += fgx * (g_sw.x * (s.albedo.x - 0.04f) + g_sw.y * (s.albedo.y - 0.04f) + g_sw.z * (s.albedo.z - 0.04f));
+        g_albedo = g_albedo + (s.rs * fgx) * g_sw;
+        const float k0 = 0.04f * om;
+        acc_fgx += g_sw.x * (k0 + s.albedo.x * s.rs) + g_sw.y * (k0 + s.albedo.y * s.rs) + g_sw.z * (k0 + s.albedo.z * s.rs);
+        acc_fgy += g_sw.x + g_sw.y + g_sw.z;
+        // specular chain: sigmoid, mip blend, texels, level, face coordinates
+        const F3 g_t = {g_Ld.x * s.Ld.x * (1.0f - s.Ld.x), g_Ld.y * s.Ld.y * (1.0f - s.Ld.y), g_Ld.z * s.Ld.z * (1.0f - s.Ld.z)};
+        float g_ro = 0.f, g_u, g_v;
+        if (s.mip.l1 != s.mip.l0) {
+            const float fm = s.mip.f;
+            if (p.chain.dL_dlevels[s.mip.l0]) scatter_bilinear(p.chain.dL_dlevels[s.mip.l0], s.b0, (1.0f - fm) * g_t);
+            if (p.chain.dL_dlevels[s.mip.l1]) scatter_bilinear(p.chain.dL_dlevels[s.mip.l1], s.b1, fm * g_t);
+            g_ro = dot(g_t, s.b1.val - s.b0.val) * s.mip.dlevel_drough;
+            g_u = dot(g_t, (1.0f - fm) * s.b0.dval_du + fm * s.b1.dval_du);
+            g_v = dot(g_t, (1.0f - fm) * s.b0.dval_dv + fm * s.b1.dval_dv);
+        } else {
+            if (p.chain.dL_dlevels[s.mip.l0]) scatter_bilinear(p.chain.dL_dlevels[s.mip.l0], s.b0, g_t);
+            g_u = dot(g_t, s.b0.dval_du);
+            g_v = dot(g_t, s.b0.dval_dv);
+        }
+        float g_rr[3];
+        face_uv_backward(s.fr, s.rr, g_u, g_v, g_rr);
+        F3 g_r;
+        {
+            const F3 grr = {g_rr[0], g_rr[1], g_rr[2]};
+            g_r = (s.rl > 1e-20f) ? (1.0f / s.rl) * (grr - dot(s.rr, grr) * s.rr) : (1.0f / s.rl) * grr;
+        }
+        // r = 2 n (n.wo) - wo ; ndv = n.wo
+        F3 g_n = (2.0f * s.ndv) * g_r;
+        const float g_ndv = 2.0f * dot(s.n, g_r);
+        g_n = g_n + g_ndv * s.wo;
+        F3 g_wo = g_ndv * s.n - g_r;
+        // diffuse map: sigmoid, texels, face coordinates of the normal
+        const F3 g_td = {g_dl.x * s.dl.x * (1.0f - s.dl.x), g_dl.y * s.dl.y * (1.0f - s.dl.y), g_dl.z * s.dl.z * (1.0f - s.dl.z)};
+        if (SMALL) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (s.bn.idx[k] < 0 || s.bn.w[k] == 0.f) continue;
+                atomicAdd(&s_acc[3 * s.bn.idx[k] + 0], s.bn.w[k] * g_td.x);
+                atomicAdd(&s_acc[3 * s.bn.idx[k] + 1], s.bn.w[k] * g_td.y);
+                atomicAdd(&s_acc[3 * s.bn.idx[k] + 2], s.bn.w[k] * g_td.z);
+            }
+        } else if (p.dL_ddiffuse_map) {
+            scatter_bilinear(p.dL_ddiffuse_map, s.bn, g_td);
+        }
+        float g_nd[3];
+        face_uv_backward(s.fn, s.n, dot(g_td, s.bn.dval_du), dot(g_td, s.bn.dval_dv), g_nd);
+        g_n = g_n + F3{g_nd[0], g_nd[1], g_nd[2]};
+        // wo = v / max(|v|, eps), v = campos - xyz
+        const F3 g_vv = (s.vl > 1e-20f) ? (1.0f / s.vl) * (g_wo - dot(s.wo, g_wo) * s.wo) : (1.0f / s.vl) * g_wo;
+        store3i(p.dL_dxyz, i, {-g_vv.x, -g_vv.y, -g_vv.z});
+        store3i(p.dL_dnormals, i, g_n);
+        store3i(p.dL_dalbedo, i, g_albedo);
+        if (p.dL_drefl_strength) p.dL_drefl_strength[i] = g_rs;
+        if (p.dL_droughness) p.dL_droughness[i] = g_ro;
+    }
+    // the shared FG pair: block sums, one atomic pair per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_fgx += __shfl_xor_sync(0xffffffffu, acc_fgx, o);
+        acc_fgy += __shfl_xor_sync(0xffffffffu, acc_fgy, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s_fg[0][threadIdx.x >> 5] = acc_fgx;
+        s_fg[1][threadIdx.x >> 5] = acc_fgy;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && p.dL_dfg) {
+        float a = 0.f, b = 0.f;
+        for (int w = 0; w < 8; ++w) { a += s_fg[0][w]; b += s_fg[1][w]; }
+        atomicAdd(p.dL_dfg, a);
+        atomicAdd(p.dL_dfg + 1, b);
+    }
+    if (SMALL) {
+        float4* out = reinterpret_cast<float4*>(p.dL_ddiffuse_map);
+        for (int k = threadIdx.x; k < texels_d; k += blockDim.x) {
+            const float x = s_acc[3 * k], y = s_acc[3 * k + 1], z = s_acc[3 * k + 2];
+            if (x != 0.f || y != 0.f || z != 0.f) atomicAdd(out + k, make_float4(x, y, z, 0.f));
+        }
+    }
+}
+
 int validate(const MrgsShadeArgs* a, const char* who, bool need_maps, int min_levels = 2) {
     if (a == nullptr) {
         set_error("%s: null args", who);
@@ -606,6 +786,32 @@ int launch_depth_normal(bool backward, int W, int H, float depth_ratio, const fl
         depth_normal_bwd_kernel<<<grid, 256, 0, stream>>>(p);
     else
         depth_normal_fwd_kernel<<<grid, 256, 0, stream>>>(p);
+    return MRGS_OK;
+}
+
+int launch_surfel_shade(const MrgsSurfelShadeArgs* a, bool backward, cudaStream_t stream) {
+    const char* who = backward ? "mrgs_surfel_shade_backward" : "mrgs_surfel_shade_forward";
+    if (a == nullptr) {
+        set_error("%s: null args", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    int st = validate(&a->chain, who, false, 2);
+    if (st != MRGS_OK) return st;
+    if (a->P < 0 || a->diffuse_res <= 0 || !a->diffuse_map || !a->fg || !a->campos ||
+        (a->P > 0 && (!a->xyz || !a->normals || !a->albedo || !a->refl_strength || !a->roughness))) {
+        set_error("%s: missing per-surfel inputs, diffuse map, fg pair or campos (P=%d)", who, a->P);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (a->P == 0) return MRGS_OK;
+    if (!backward) {
+        surfel_shade_fwd_kernel<<<(a->P + 255) / 256, 256, 0, stream>>>(*a);
+        return MRGS_OK;
+    }
+    const unsigned blocks = (unsigned)std::min<long long>(((long long)a->P + 255) / 256, 148 * 4);
+    if (a->dL_ddiffuse_map != nullptr && 6 * a->diffuse_res * a->diffuse_res <= kSmallTexels)
+        surfel_shade_bwd_kernel<true><<<blocks, 256, 0, stream>>>(*a);
+    else
+        surfel_shade_bwd_kernel<false><<<blocks, 256, 0, stream>>>(*a);
     return MRGS_OK;
 }
 

@@ -272,35 +272,95 @@ def _fg_of_first_surfel(ndotv, roughness):
     return fg[0, :, 0, 0]                                     # [2]
 
 
+class _SurfelShade(torch.autograd.Function):
+    """(xyz, normals, albedo, refl, rough [P,*], fg [2], campos [3], diffuse_map, *levels) ->
+    (diffuse, specular, direct_light) [P,3]; mrgs_surfel_shade_forward / _backward."""
+
+    @staticmethod
+    def forward(ctx, xyz, normals, albedo, refl, rough, fg, campos, cfg, diffuse_map, *levels):
+        lib = _lib.load()
+        if not xyz.is_cuda:
+            raise RuntimeError("get_full_color_volume: tensors must be CUDA tensors")
+        ctx.set_materialize_grads(False)
+        t = [x.detach().contiguous().float() for x in (xyz, normals, albedo, refl, rough, fg, campos, diffuse_map)]
+        lv = [l.detach().contiguous() for l in levels]
+        P, dev = t[0].shape[0], t[0].device
+        a = _lib.SurfelShadeArgs()
+        a.chain = _chain_args(lv, cfg[0], cfg[1])
+        a.P, a.diffuse_res = P, int(t[7].shape[1])
+        (a.xyz, a.normals, a.albedo, a.refl_strength, a.roughness, a.fg, a.campos, a.diffuse_map) = (x.data_ptr() for x in t)
+        outs = [torch.empty((P, 3), dtype=torch.float32, device=dev) for _ in range(3)]
+        a.diffuse, a.specular, a.direct_light = (o.data_ptr() for o in outs)
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_surfel_shade_forward(C.byref(a), _stream(dev)), "mrgs_surfel_shade_forward")
+        ctx.cfg = cfg
+        ctx.save_for_backward(*t, *lv)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, g_diffuse, g_specular, g_direct):
+        lib = _lib.load()
+        xyz, normals, albedo, refl, rough, fg, campos, diffuse_map, *lv = ctx.saved_tensors
+        P, dev = xyz.shape[0], xyz.device
+        a = _lib.SurfelShadeArgs()
+        a.chain = _chain_args(lv, ctx.cfg[0], ctx.cfg[1])
+        a.P, a.diffuse_res = P, int(diffuse_map.shape[1])
+        (a.xyz, a.normals, a.albedo, a.refl_strength, a.roughness, a.fg, a.campos, a.diffuse_map) = (
+            x.data_ptr() for x in (xyz, normals, albedo, refl, rough, fg, campos, diffuse_map))
+        keep = [None if g is None else g.contiguous().float() for g in (g_diffuse, g_specular, g_direct)]
+        a.dL_ddiffuse, a.dL_dspecular, a.dL_ddirect = (None if g is None else g.data_ptr() for g in keep)
+        need = ctx.needs_input_grad
+        grads = [torch.empty_like(x) if need[i] else None for i, x in enumerate((xyz, normals, albedo, refl, rough))]
+        a.dL_dxyz, a.dL_dnormals, a.dL_dalbedo, a.dL_drefl_strength, a.dL_droughness = (
+            None if g is None else g.data_ptr() for g in grads)
+        g_fg = torch.zeros(2, dtype=torch.float32, device=dev) if need[5] else None
+        a.dL_dfg = None if g_fg is None else g_fg.data_ptr()
+        n_d = diffuse_map.shape[0] * diffuse_map.shape[1] * diffuse_map.shape[2]
+        d4 = torch.zeros((n_d, 4), dtype=torch.float32, device=dev) if need[8] else None
+        a.dL_ddiffuse_map = None if d4 is None else d4.data_ptr()
+        counts = [l.shape[0] * l.shape[1] * l.shape[2] for l in lv]
+        need_l = [need[9 + i] for i in range(len(lv))]
+        flat4 = torch.zeros((sum(counts), 4), dtype=torch.float32, device=dev) if any(need_l) else None
+        off = 0
+        for i, n in enumerate(counts):
+            if need_l[i]:
+                a.chain.dL_dlevels[i] = flat4.data_ptr() + off * 16
+            off += n
+        with torch.cuda.device(dev):
+            _lib.check(lib.mrgs_surfel_shade_backward(C.byref(a), _stream(dev)), "mrgs_surfel_shade_backward")
+        g_levels, off = [], 0
+        for l, n, nd in zip(lv, counts, need_l):
+            g_levels.append(flat4[off:off + n, :3].reshape(l.shape) if nd else None)
+            off += n
+        g_dmap = None if d4 is None else d4[:, :3].reshape(diffuse_map.shape)
+        return (*grads, g_fg, None, None, g_dmap, *g_levels)
+
+
+def _surfel_colours(envmap: "EnvLight", xyz, albedo, R, T, normal_map, refl_strength, roughness):
+    """(diffuse, specular, direct_light) [N,3]: one fused kernel pair for everything per-surfel; the FG pair of the first
+    surfel (the reference's `fg[0]`, see _fg_of_first_surfel) is evaluated in torch so its gradient reaches surfel 0."""
+    rays_o = _camera_origin(R, T, xyz.device)
+    w_o0 = safe_normalize(rays_o[None] - xyz[0:1])
+    fg = _fg_of_first_surfel(torch.sum(w_o0 * normal_map[0:1], dim=-1, keepdim=True), roughness[0:1])
+    return _SurfelShade.apply(xyz, normal_map, albedo, refl_strength, roughness, fg, rays_o,
+                              (envmap.min_roughness, envmap.max_roughness), envmap.diffuse, *envmap.specular)
+
+
 def get_full_color_volume(envmap: "EnvLight", xyz, albedo, HWK, R, T, normal_map, render_alpha, scaling_modifier=1.0,
                           refl_strength=None, roughness=None):
     """utils/refl_utils.py:426-447 — per-SURFEL split-sum colours (the volume-rendering stage): (diffuse, specular) [N,3]."""
-    rays_o = _camera_origin(R, T, xyz.device).expand(normal_map.shape[0], -1)
-    w_o = safe_normalize(rays_o - xyz)
-    NdotV = torch.sum(w_o * normal_map, dim=-1, keepdim=True)
-    rays_refl = safe_normalize(2 * normal_map * NdotV - w_o)
-    fg = _fg_of_first_surfel(NdotV, roughness)
-    diffuse = envmap(normal_map, mode="diffuse") * (1 - refl_strength) * albedo
-    specular = envmap(rays_refl, roughness=roughness) * ((0.04 * (1 - refl_strength) + albedo * refl_strength) * fg[0:1] + fg[1:2])
+    diffuse, specular, _ = _surfel_colours(envmap, xyz, albedo, R, T, normal_map, refl_strength, roughness)
     return diffuse, specular
 
 
 def get_full_color_volume_indirect(envmap: "EnvLight", xyz, albedo, HWK, R, T, normal_map, render_alpha,
                                    scaling_modifier=1.0, refl_strength=None, roughness=None, pc=None, indirect_light=None):
-    """utils/refl_utils.py:450-490 with visibility = 1 (the mesh/OptiX tracer stays on the reference)."""
+    """utils/refl_utils.py:450-490 with visibility = 1 (the mesh/OptiX tracer stays on the reference): the specular light
+    is then the direct light alone, `indirect_light` only rides along as a feature."""
     if pc is not None and getattr(pc, "ray_tracer", None) is not None:
         raise NotImplementedError("mesh/OptiX visibility tracing stays on the reference")
-    rays_o = _camera_origin(R, T, xyz.device).expand(normal_map.shape[0], -1)
-    w_o = safe_normalize(rays_o - xyz)
-    NdotV = torch.sum(w_o * normal_map, dim=-1, keepdim=True)
-    rays_refl = safe_normalize(2 * normal_map * NdotV - w_o)
-    visibility = torch.ones_like(render_alpha)
-    fg = _fg_of_first_surfel(NdotV, roughness)
-    diffuse = envmap(normal_map, mode="diffuse") * (1 - refl_strength) * albedo
-    direct_light = envmap(rays_refl, roughness=roughness)
-    specular_weight = (0.04 * (1 - refl_strength) + albedo * refl_strength) * fg[0:1] + fg[1:2]
-    specular_light = direct_light * visibility + (1 - visibility) * indirect_light
-    return diffuse, specular_light * specular_weight, {"visibility": visibility, "direct_light": direct_light}
+    diffuse, specular, direct_light = _surfel_colours(envmap, xyz, albedo, R, T, normal_map, refl_strength, roughness)
+    return diffuse, specular, {"visibility": torch.ones_like(render_alpha), "direct_light": direct_light}
 
 
 class EnvLight(torch.nn.Module):

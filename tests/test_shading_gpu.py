@@ -234,3 +234,49 @@ def test_level_grad_sink_equals_per_view_autograd_accumulation():
         assert _rel(a, b) <= 1e-5
     for a, b in zip(a_f, b_f):
         assert torch.equal(a, b)
+
+
+def test_per_surfel_volume_colours_forward_backward():
+    """get_full_color_volume (utils/refl_utils.py:426-447) as the fused mrgs_surfel_shade_* pair against the torch
+    restatement: values 1e-5, gradients of every per-surfel input, of the diffuse map and of the chain; includes the
+    reference's `fg[0]` quirk (the FIRST surfel's LUT pair multiplies every surfel, its gradient lands on surfel 0)."""
+    from materialrefgs_b200.shading import get_full_color_volume
+    N = 30_000
+    g = torch.Generator().manual_seed(11)
+    cam = synthetic.orbit_camera(2, 8, 64, 64)
+    levels = so.synthetic_chain(64, 16, device=DEV)
+    diffuse_map = 0.7 * torch.randn(6, 16, 16, 3, generator=g).to(DEV)
+    base = dict(xyz=1.3 * (2 * torch.rand(N, 3, generator=g) - 1), n=torch.nn.functional.normalize(torch.randn(N, 3, generator=g), dim=-1),
+                albedo=torch.rand(N, 3, generator=g), rs=torch.rand(N, 1, generator=g), ro=torch.rand(N, 1, generator=g) * 1.2 - 0.1)
+    w_d, w_s = torch.randn(N, 3, generator=g).to(DEV), torch.randn(N, 3, generator=g).to(DEV)
+
+    def run(fn):
+        t = {k: v.to(DEV).clone().requires_grad_(True) for k, v in base.items()}
+        lv = [l.clone().requires_grad_(True) for l in levels]
+        dm = diffuse_map.clone().requires_grad_(True)
+        d, s = fn(t, lv, dm)
+        ((d * w_d).sum() + (s * w_s).sum()).backward()
+        return d.detach(), s.detach(), {k: v.grad for k, v in t.items()}, [l.grad for l in lv], dm.grad
+
+    def ours(t, lv, dm):
+        env = _env(lv)
+        env.diffuse = dm
+        return get_full_color_volume(env, t["xyz"], t["albedo"], cam.HWK, cam.R, cam.T, t["n"], None,
+                                     refl_strength=t["rs"], roughness=t["ro"])
+
+    def oracle(t, lv, dm):
+        return so.get_full_color_volume(so.EnvLightOracle(lv, diffuse=dm), so.load_lut(DEV), t["xyz"], t["albedo"], cam, t["n"],
+                                        t["rs"], t["ro"])
+    od, os_, og, olv, odm = run(ours)
+    rd, rs_, rg, rlv, rdm = run(oracle)
+    assert (od - rd).abs().max().item() <= 1e-5 and (os_ - rs_).abs().max().item() <= 1e-5
+    for k in base:
+        l1 = ((og[k] - rg[k]).abs().sum() / rg[k].abs().sum()).item()
+        frac = ((og[k] - rg[k]).abs() > 1e-2 * rg[k].abs().max()).float().mean().item()
+        assert l1 <= 2e-3 and frac <= 1e-3, (k, l1, frac)
+    # surfel 0 carries the gradient of the shared FG pair: compare it on its own
+    for k in ("n", "ro", "xyz"):
+        assert _rel(og[k][0], rg[k][0]) <= 2e-3, k
+    assert _rel(odm, rdm) <= 1e-3
+    for a, b in zip(olv, rlv):
+        assert _rel(a, b) <= 1e-3
