@@ -39,3 +39,30 @@ for P in (1_000_000, 5_000_000):
         (out * w).sum().backward()
     print(f"P={P}: diffuse query fwd+bwd {timeit(lambda: run('diffuse')):.3f} ms, "
           f"specular (6-level chain) fwd+bwd {timeit(lambda: run(None)):.3f} ms")
+
+# get_full_color_volume: the fused per-surfel kernel pair vs the same chain in eager torch (the oracle's restatement on the GPU)
+from materialrefgs_b200 import synthetic  # noqa: E402
+from materialrefgs_b200.shading import get_full_color_volume  # noqa: E402
+from oracle import shading_oracle as so  # noqa: E402
+
+cam = synthetic.orbit_camera(2, 8, 64, 64)
+oracle_env = so.EnvLightOracle(levels, diffuse=env.diffuse)
+lut = so.load_lut(dev)
+for P in (1_000_000,):
+    g = torch.Generator(device=dev).manual_seed(3)
+    t = dict(xyz=1.3 * (2 * torch.rand(P, 3, device=dev, generator=g) - 1),
+             n=torch.nn.functional.normalize(torch.randn(P, 3, device=dev, generator=g), dim=-1),
+             albedo=torch.rand(P, 3, device=dev, generator=g), rs=torch.rand(P, 1, device=dev, generator=g),
+             ro=torch.rand(P, 1, device=dev, generator=g))
+    t = {k: v.requires_grad_(True) for k, v in t.items()}
+    w = torch.randn(P, 3, device=dev)
+
+    def fused():
+        d, s = get_full_color_volume(env, t["xyz"], t["albedo"], cam.HWK, cam.R, cam.T, t["n"], None, refl_strength=t["rs"],
+                                     roughness=t["ro"])
+        ((d + s) * w).sum().backward()
+
+    def eager():
+        d, s = so.get_full_color_volume(oracle_env, lut, t["xyz"], t["albedo"], cam, t["n"], t["rs"], t["ro"])
+        ((d + s) * w).sum().backward()
+    print(f"P={P}: get_full_color_volume fwd+bwd fused {timeit(fused):.3f} ms, eager torch {timeit(eager, n=5):.3f} ms")
