@@ -229,10 +229,14 @@ class OursStep:
             if self.world > 1:
                 self.arena.accumulate_view({}, self.means2D.grad, self.last["radii"])
             if e2e:  # device -> host: the rendered image and the loss of every view (copy stream, pinned target)
-                self._e2e_readback(v, loss)
+                self._e2e_readback(i & 1, v, loss)
         if e2e:
-            self.copy_stream.synchronize()
-            total = float(sum(float(self.loss_host[v]) + float(self.img_host[v][0, 0, 0]) for v in range(V)))
+            # results are consumed like a training loop logs them: step i's copies are in flight while step i+1 is
+            # enqueued; the host waits for (and reads) the PREVIOUS step's image + losses here, the last step's in
+            # e2e_finish() — every step's result is read inside the timed region, the pipeline never drains
+            self.result_events[i & 1].record(self.copy_stream)
+            total = self._e2e_consume((i & 1) ^ 1)
+            self.result_pending[i & 1] = True
         if self.world > 1:                 # autograd accumulated in place: no flattening copy
             self.arena.allreduce(extra=(self.level_sink,) if self.level_sink is not None else ())
         if self.level_sink is not None:
@@ -248,9 +252,12 @@ class OursStep:
         self.in_events = [torch.cuda.Event(), torch.cuda.Event()]
         self.free_events = [None, None]
         self.slot = 0
-        self.img_host = [torch.empty((3, WORKLOAD["H"], WORKLOAD["W"]), dtype=torch.float32).pin_memory()
-                         for _ in range(VIEWS_PER_RANK)]
-        self.loss_host = torch.empty(VIEWS_PER_RANK, dtype=torch.float32).pin_memory()
+        # two sets of pinned result buffers (step parity): one is read by the host while the other is being filled
+        self.img_host = [[torch.empty((3, WORKLOAD["H"], WORKLOAD["W"]), dtype=torch.float32).pin_memory()
+                          for _ in range(VIEWS_PER_RANK)] for _ in range(2)]
+        self.loss_host = [torch.empty(VIEWS_PER_RANK, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.result_events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.result_pending = [False, False]
 
     def _e2e_prefetch(self, view):
         self._e2e_init()
@@ -272,7 +279,7 @@ class OursStep:
         self.taken = k
         return self.in_slots[k]
 
-    def _e2e_readback(self, v, loss):
+    def _e2e_readback(self, par, v, loss):
         main = torch.cuda.current_stream(self.dev)
         done = torch.cuda.Event()
         done.record(main)
@@ -280,9 +287,21 @@ class OursStep:
         img = self.last["render"].detach()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(done)
-            self.img_host[v].copy_(img, non_blocking=True)
-            self.loss_host[v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            self.img_host[par][v].copy_(img, non_blocking=True)
+            self.loss_host[par][v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         img.record_stream(self.copy_stream)
+
+    def _e2e_consume(self, par):
+        """Wait for the result copies of the step with parity `par` and read them on the host."""
+        if not self.result_pending[par]:
+            return 0.0
+        self.result_events[par].synchronize()
+        self.result_pending[par] = False
+        return float(sum(float(self.loss_host[par][v]) + float(self.img_host[par][v][0, 0, 0])
+                         for v in range(VIEWS_PER_RANK)))
+
+    def e2e_finish(self):
+        return self._e2e_consume(0) + self._e2e_consume(1)
 
     def h2d_bytes(self):
         return VIEWS_PER_RANK * (sum(v.numel() * 4 for v in self.up_host.values()) + (16 + 16 + 3) * 4)
@@ -467,10 +486,12 @@ def main():
     # ---- end-to-end timing: pinned host inputs -> device, result -> host, every step ----------
     for i in range(2):
         stepper.step(i, e2e=True)
+    stepper.e2e_finish()
     barrier(world_eff)
     t0 = time.perf_counter()
     for i in range(a.steps):
         stepper.step(a.warmup + i, e2e=True)
+    stepper.e2e_finish()          # the last step's results are read inside the timed region too
     barrier(world_eff)
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / a.steps
     if world_eff > 1:
@@ -495,7 +516,7 @@ def main():
                    "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient arenas) exceeds the 126 MB L2"},
         "e2e": {"value": world_eff * VIEWS_PER_RANK * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
                 "d2h_bytes_per_step": stepper.d2h_bytes(),
-                "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss read back; surfel parameters are model state resident in HBM"},
+                "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss of every view read back to pinned host memory and consumed by the host one step later (double-buffered, like asynchronous logging), the last step's before the clock stops; surfel parameters are model state resident in HBM"},
         "clocks": clocks,
     }
     if a.impl == "reference":
