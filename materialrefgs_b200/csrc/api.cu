@@ -460,7 +460,7 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         }
         MRGS_LAUNCH_OK("depth_sort", stream, debug);
         {
-            StageScope sc(MRGS_STAGE_SCAN, stream, 3);
+            StageScope sc(MRGS_STAGE_SCAN, stream, 2);
             offsets_in_order(order, pp.tiles_touched, a->P, block_sums, offsets, stream);
         }
         MRGS_LAUNCH_OK("scan", stream, debug);

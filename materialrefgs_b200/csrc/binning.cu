@@ -148,40 +148,6 @@ radix_row_scan_kernel(uint32_t* __restrict__ block_hist, const uint32_t* __restr
     }
 }
 
-// exclusive scan of `n` uint32 in place by ONE CTA (used for the few hundred scan block sums)
-__global__ void __launch_bounds__(1024) exclusive_scan_kernel(uint32_t* __restrict__ data, int n) {
-    __shared__ uint32_t s_warp[32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int seg = (n + 1023) / 1024;
-    const int lo = min(n, (int)threadIdx.x * seg), hi = min(n, lo + seg);
-    uint32_t mine = 0;
-    for (int i = lo; i < hi; ++i) mine += data[i];
-    uint32_t incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t t = __shfl_up_sync(kFullMask, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = s_warp[lane];
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t t = __shfl_up_sync(kFullMask, w, d);
-            if (lane >= d) w += t;
-        }
-        s_warp[lane] = w;  // inclusive over warps
-    }
-    __syncthreads();
-    uint32_t run = (warp ? s_warp[warp - 1] : 0u) + (incl - mine);
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t v = data[i];
-        data[i] = run;
-        run += v;
-    }
-}
-
 // Digit histograms of ALL passes from one read of the keys: hist[pass][digit] (global totals).
 struct PassPlan {
     int passes;
@@ -525,10 +491,22 @@ gather_reduce_kernel(const uint32_t* __restrict__ order, const uint32_t* __restr
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
 }
 
+// `block_sums` are the RAW per-block totals of gather_reduce_kernel: every block adds up the totals of the blocks
+// before it on its own (a few hundred values, one or two per thread) — no separate scan launch in between.
 __global__ void __launch_bounds__(kScanThreads)
 gather_scan_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched, int n,
-                   const uint32_t* __restrict__ block_offsets, uint32_t* __restrict__ offsets_incl) {
+                   const uint32_t* __restrict__ block_sums, uint32_t* __restrict__ offsets_incl) {
     __shared__ uint32_t s_warp[kScanThreads / 32];
+    __shared__ uint32_t s_before[kScanThreads / 32];
+    uint32_t before = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += kScanThreads) before += block_sums[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(kFullMask, before, o);
+    if ((threadIdx.x & 31) == 0) s_before[threadIdx.x >> 5] = before;
+    __syncthreads();
+    uint32_t block_offset = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; ++w) block_offset += s_before[w];
     const int base = blockIdx.x * kScanChunk + threadIdx.x * kScanItems;
     uint32_t v[kScanItems];
     uint32_t mine = 0;
@@ -538,7 +516,7 @@ gather_scan_kernel(const uint32_t* __restrict__ order, const uint32_t* __restric
         mine += v[k];
     }
     uint32_t total;
-    uint32_t run = block_offsets[blockIdx.x] + block_exclusive_scan_256(mine, s_warp, total);
+    uint32_t run = block_offset + block_exclusive_scan_256(mine, s_warp, total);
 #pragma unroll
     for (int k = 0; k < kScanItems; ++k) {
         run += v[k];
@@ -650,7 +628,6 @@ int offsets_in_order(const uint32_t* order, const uint32_t* tiles_touched, int P
                      uint32_t* offsets_incl, cudaStream_t stream) {
     const int nb = scan_blocks(P);
     gather_reduce_kernel<<<nb, kScanThreads, 0, stream>>>(order, tiles_touched, P, block_sums);
-    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(block_sums, nb);
     gather_scan_kernel<<<nb, kScanThreads, 0, stream>>>(order, tiles_touched, P, block_sums, offsets_incl);
     return MRGS_OK;
 }
