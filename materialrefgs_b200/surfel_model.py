@@ -6,6 +6,8 @@ in order to run an actual loop around the rasterizer:
   * the `.ply` attribute order and per-field transposes                         (:462-523 save_ply, :725-836 load_ply)
   * densification statistics, clone / split / prune, Adam-state surgery         (:856-1061)
   * reset_opacity0                                                              (:531-534)
+  * the checkpoint tuple of capture() / restore() (`chkpnt<iter>.pth`)           (:124-172)
+  * the position learning-rate schedule                                         (:455-460, utils/general_utils.py:29-63)
 Pinned by tests/golden/densify_*.npz, produced by the reference's own methods (tests/golden/make_golden_densify.py).
 
 Multi-GPU: every rank holds the full store. After `GradArena.allreduce()` the statistics are identical on all ranks;
@@ -206,10 +208,35 @@ def build_rotation(r: torch.Tensor) -> torch.Tensor:
     return R
 
 
+def get_expon_lr_func(lr_init, lr_final, lr_delay_steps=0, lr_delay_mult=1.0, max_steps=1000000):
+    """utils/general_utils.py:29-63: log-linear interpolation from lr_init to lr_final, optionally eased in."""
+    def helper(step):
+        if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+            return 0.0
+        if lr_delay_steps > 0:
+            delay_rate = lr_delay_mult + (1 - lr_delay_mult) * np.sin(0.5 * np.pi * np.clip(step / lr_delay_steps, 0, 1))
+        else:
+            delay_rate = 1.0
+        t = np.clip(step / max_steps, 0, 1)
+        return delay_rate * np.exp(np.log(lr_init) * (1 - t) + np.log(lr_final) * t)
+    return helper
+
+
+# order of the parameter entries in the checkpoint tuple (gaussian_model.py:124-148), after active_sh_degree
+_CAPTURE_ORDER = ("xyz", "refl_strength", "metalness", "roughness", "ori_color", "diffuse_color", "features_dc",
+                  "features_rest", "indirect_dc", "indirect_rest", "indirect_asg", "scaling", "rotation", "opacity",
+                  "normal1", "normal2")
+
+
 class SurfelStore:
     """Parameters, Adam optimizer and densification statistics of a surfel cloud (GaussianModel's bookkeeping)."""
+    max_sh_degree = 3
 
-    def __init__(self, fields: dict, lrs: dict | None = None, percent_dense: float = 0.01, frozen=("normal1", "normal2")):
+    def __init__(self, fields: dict, lrs: dict | None = None, percent_dense: float = 0.01, frozen=("normal1", "normal2"),
+                 spatial_lr_scale: float = 1.0, active_sh_degree: int = 0, xyz_schedule: dict | None = None):
+        self.spatial_lr_scale = spatial_lr_scale
+        self.active_sh_degree = active_sh_degree
+        self.xyz_scheduler_args = get_expon_lr_func(**xyz_schedule) if xyz_schedule else None
         dev = fields["xyz"].device if isinstance(fields["xyz"], torch.Tensor) else torch.device("cpu")
         self.params: dict[str, nn.Parameter] = {}
         for name in FIELDS:
@@ -342,6 +369,54 @@ class SurfelStore:
         """:531-534."""
         new = inverse_sigmoid(torch.min(self.get_opacity, torch.ones_like(self.get_opacity) * 0.01)).detach()
         self.replace_tensor_to_optimizer("opacity", new)
+
+    # -- schedule (gaussian_model.py:455-460, :311-313)
+    def update_learning_rate(self, iteration):
+        if self.xyz_scheduler_args is None:
+            return None
+        for group in self.optimizer.param_groups:
+            if group["name"] == "xyz":
+                group["lr"] = self.xyz_scheduler_args(iteration)
+                return group["lr"]
+
+    def oneupSHdegree(self):
+        if self.active_sh_degree < self.max_sh_degree:
+            self.active_sh_degree += 1
+
+    # -- checkpoint tuple (gaussian_model.py:124-172); train_refnerf.py saves torch.save((capture(), iteration), path)
+    def capture(self):
+        return (self.active_sh_degree, *[self.params[n] for n in _CAPTURE_ORDER], self.max_radii2D,
+                self.xyz_gradient_accum, self.denom, self.optimizer.state_dict(), self.spatial_lr_scale)
+
+    @classmethod
+    def restore(cls, model_args, lrs: dict | None = None, device=None, **kw):
+        """A store from the reference's checkpoint tuple. The optimizer state is loaded as saved; like the reference
+        (:169) the anisotropic-Gaussian parameters are re-created as zeros."""
+        if len(model_args) != len(_CAPTURE_ORDER) + 6:
+            raise ValueError(f"checkpoint tuple has {len(model_args)} entries, expected {len(_CAPTURE_ORDER) + 6}")
+        active_sh_degree, *rest = model_args
+        tensors = dict(zip(_CAPTURE_ORDER, rest[:len(_CAPTURE_ORDER)]))
+        max_radii2D, xyz_gradient_accum, denom, opt_dict, spatial_lr_scale = rest[len(_CAPTURE_ORDER):]
+        device = device if device is not None else tensors["xyz"].device
+        fields = {n: t.detach().to(device) for n, t in tensors.items()}
+        fields["indirect_asg"] = torch.zeros((fields["rotation"].shape[0], 32, 5), device=device)
+        st = cls(fields, lrs=lrs, spatial_lr_scale=spatial_lr_scale, active_sh_degree=active_sh_degree, **kw)
+        st.max_radii2D = max_radii2D.to(device)
+        st.xyz_gradient_accum = xyz_gradient_accum.to(device)
+        st.denom = denom.to(device)
+        # the reference's optimizer also holds the two environment maps (groups "env", "env2"): take the per-surfel
+        # groups by NAME, whatever their position in the saved state dict
+        by_name = {g["name"]: g for g in opt_dict["param_groups"]}
+        for group in st.optimizer.param_groups:
+            saved = by_name.get(group["name"])
+            if saved is None:
+                continue
+            group["lr"] = saved["lr"]
+            state = opt_dict["state"].get(saved["params"][0])
+            if state is not None:
+                st.optimizer.state[group["params"][0]] = {
+                    k: (v.detach().clone().to(device) if isinstance(v, torch.Tensor) else v) for k, v in state.items()}
+        return st
 
     # -- formats
     def save_ply(self, path):

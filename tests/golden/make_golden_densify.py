@@ -173,5 +173,27 @@ def main():
         print("wrote", path, "P", P, "->", after["p_xyz"].shape[0])
 
 
+def checkpoint_and_schedule():
+    """A small checkpoint written the way train_refnerf.py does it (torch.save((gaussians.capture(), iteration), path),
+    scene/gaussian_model.py:124-148) and samples of the reference's learning-rate schedule (general_utils.py:29-63)."""
+    from utils.general_utils import get_expon_lr_func
+    P, seed = 12, 9
+    m, args = make_reference_model(initial_fields(P, seed), 0.01)
+    adam_warmup([getattr(m, a) for a in FIELDS], m.optimizer, 3, seed + 1)
+    m.active_sh_degree = 2
+    m.spatial_lr_scale = 3.5
+    m.xyz_gradient_accum += 0.25
+    m.denom += 2
+    m.max_radii2D += 7
+    torch.save((m.capture(), 1234), ROOT / "tests" / "golden" / "chkpnt_reference_small.pth")
+    steps = np.array([-1, 0, 1, 10, 500, 7000, 29999, 30000, 45000], dtype=np.int64)
+    f1 = get_expon_lr_func(lr_init=1.6e-4 * 3.5, lr_final=1.6e-6 * 3.5, lr_delay_mult=0.01, max_steps=30000)
+    f2 = get_expon_lr_func(lr_init=0.01, lr_final=0.001, lr_delay_steps=1000, lr_delay_mult=0.1, max_steps=20000)
+    np.savez(ROOT / "tests" / "golden" / "lr_schedule.npz", steps=steps, plain=np.array([f1(int(s)) for s in steps]),
+             delayed=np.array([f2(int(s)) for s in steps]))
+    print("wrote chkpnt_reference_small.pth, lr_schedule.npz")
+
+
 if __name__ == "__main__":
     main()
+    checkpoint_and_schedule()
