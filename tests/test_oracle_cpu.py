@@ -9,6 +9,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
+from materialrefgs_b200 import synthetic
 from oracle import surfel_oracle as so
 
 ROOT = Path(__file__).resolve().parent.parent
@@ -150,3 +151,24 @@ def test_synthetic_generator_is_deterministic():
     cam = synthetic.orbit_camera(1, 8, 800, 800)
     assert abs(cam.K[0, 0] - 800 / (2 * np.tan(0.6911 / 2))) < 1e-3
     assert np.allclose(cam.world_view_transform.numpy()[:3, :3].T @ cam.R, np.eye(3), atol=1e-5)
+
+
+def test_synthetic_cameras_follow_the_reference_conventions():
+    """tests/golden/camera_matrices.npz comes from the reference's own utils/graphics_utils.py composed as
+    scene/cameras.py:70-84 does (make_golden_cameras.py): transposed world-to-view, projection, their product, the
+    camera centre and the pinhole focal lengths of the synthetic views used everywhere in tests / bench / tools."""
+    z = np.load(ROOT / "tests" / "golden" / "camera_matrices.npz")
+    k = 0
+    while f"view{k}" in z.files:
+        i, n, W, H, radius = z[f"view{k}"]
+        cam = synthetic.orbit_camera(int(i), int(n), int(W), int(H), radius=float(radius))
+        # getWorld2View2 inverts the pose twice (translate = 0, scale = 1): equal up to float32 rounding of that round trip
+        assert np.allclose(cam.world_view_transform.numpy(), z[f"w2v{k}"], atol=1e-6)
+        assert np.allclose(cam.full_proj_transform.numpy(), z[f"full{k}"], atol=1e-5)
+        assert np.allclose(cam.camera_center.numpy(), z[f"center{k}"], atol=1e-5)
+        K = np.asarray(cam.HWK[2], np.float64)
+        assert np.allclose([K[0, 0], K[1, 1]], z[f"focal{k}"], rtol=1e-6)
+        # principal point at the image centre: the K-based projection the reference uses when HWK is given is the same
+        assert np.allclose(z[f"projK{k}"], z[f"proj{k}"], atol=1e-6)
+        k += 1
+    assert k == 3
