@@ -1,10 +1,14 @@
 """Torch restatement of the reference's deferred split-sum shading. TEST INFRASTRUCTURE ONLY
 (only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import it).
 
-PARITY UNPINNED: the reference's shading runs through nvdiffrast's `dr.texture`, which is neither
-vendored under /root/reference (requirements.txt:57 is a local file:// path without a version) nor
-installed here, and the reference has no test or golden image for this path. This
-file therefore restates (a) the reference's own torch code line by line and (b) nvdiffrast's
+PARITY UNPINNED FOR THE TEXEL FETCH ONLY: the reference's shading runs through nvdiffrast's `dr.texture`, which
+is neither vendored under /root/reference (requirements.txt:57 is a local file:// path without a version) nor
+installed here, and the reference has no test or golden image for this path. Everything AROUND the
+fetch is pinned: tests/golden/shading_*.npz hold outputs and gradients of the reference's OWN
+get_specular_color_surfel / get_full_color_volume / sample_camera_rays / reflection / EnvLight.__call__ / get_mip,
+run on the CPU with `dr.texture` supplied by lut_fetch / cube_texture below (tests/golden/make_golden_shading.py), and
+tests/golden/depth_normal_*.npz those of utils/point_utils.py (make_golden_depth_normal.py); tests/test_shading_oracle_cpu.py
+holds this file to them at 1e-6. This file restates (a) the reference's own torch code line by line and (b) nvdiffrast's
 published texture semantics from memory of its texture.cu: texel centres at (i+0.5)/size,
 `u*size-0.5` taps, clamp-to-edge for 2-D "clamp" mode, seamless cube faces with the missing corner
 tap replaced by the mean of the other three, mip level = clamp(bias,0,L-1) blended linearly.
