@@ -1,5 +1,6 @@
-"""GPU: the whole render() contract of gaussian_renderer/__init__.py:225-469 (render_surfel) — our kernels against
-the reference rasterizer extension + the torch restatement of its shading/regularisers, on a duck-typed model."""
+"""GPU: the whole render() contract of gaussian_renderer/__init__.py (render_initial, render_surfel, render_volume) — our
+kernels against oracle/render_oracle.py driven by the reference rasterizer extension. That restatement is pinned on the
+CPU by vectors of the reference's OWN three functions (tests/test_render_oracle_cpu.py)."""
 import math
 import types
 
@@ -8,7 +9,8 @@ import torch
 import torch.nn.functional as F
 
 from materialrefgs_b200 import synthetic
-from materialrefgs_b200.render import eval_sh, render_surfel
+from materialrefgs_b200.render import render_surfel
+from oracle import render_oracle as ro
 from oracle import shading_oracle as so
 
 pytestmark = pytest.mark.gpu
@@ -46,26 +48,20 @@ class FakeModel:
         return n * torch.where(flip, 1.0, -1.0)
 
 
+class OracleSide:
+    """The same model seen by the oracle: every getter of `pc`, but the environment light is the torch restatement."""
+    def __init__(self, pc, env):
+        self._pc, self._env = pc, env
+
+    def __getattr__(self, k):
+        if k in ("get_envmap", "get_envmap_2"):
+            return self._env
+        return getattr(self._pc, k)
+
+
 def reference_pipeline(ref_ext, cam, pc, pipe, bg, levels):
-    """Same contract with the reference rasterizer + torch restatements of everything after it."""
-    means3D = pc.get_xyz
-    m2d = torch.zeros_like(means3D, requires_grad=True)
-    rs = ref_ext.GaussianRasterizationSettings(
-        cam.image_height, cam.image_width, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), torch.zeros_like(bg), 1.0,
-        cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center, False, False)
-    d = means3D - cam.camera_center
-    d = d / d.norm(dim=1, keepdim=True)
-    n = pc.get_normal(1.0, d)
-    refl = 2 * torch.sum(n * -d, dim=1, keepdim=True) * n + d
-    ind = torch.clamp_min(eval_sh(3, pc.get_indirect.transpose(1, 2).view(-1, 3, 16), refl), 0.0)
-    feats = torch.cat((pc.get_refl, pc.get_rough, pc.get_ori_color, ind), -1)
-    _, color, feat, radii, allmap = ref_ext.GaussianRasterizer(rs)(
-        means3D=means3D, means2D=m2d, opacities=pc.get_opacity, shs=pc.get_features, features=feats,
-        scales=pc.get_scaling, rotations=pc.get_rotation)
-    out = so.shade_surfel(so.EnvLightOracle(levels), so.load_lut(DEV), color, feat, allmap, cam, bg)
-    out["surf_depth"], out["surf_normal"] = so.surf_depth_normal(allmap, cam, pipe.depth_ratio)
-    out["radii"], out["rend_dist"] = radii, allmap[6:7]
-    return out
+    """render_surfel with the reference rasterizer + the pinned torch restatement of everything after it."""
+    return ro.render_surfel(ref_ext, cam, OracleSide(pc, so.EnvLightOracle(levels)), pipe, bg)
 
 
 def test_render_surfel_contract(ref_ext):
@@ -199,20 +195,6 @@ def test_render_surfel_contract_raw_parameters(ref_ext):
 
 
 # ---- render_initial / render_volume (gaussian_renderer/__init__.py:94-222, :521-745) -----------------------------
-def _raster_ref(ref_ext, cam, bg, **kw):
-    rs = ref_ext.GaussianRasterizationSettings(
-        cam.image_height, cam.image_width, math.tan(cam.FoVx * 0.5), math.tan(cam.FoVy * 0.5), torch.zeros_like(bg), 1.0,
-        cam.world_view_transform, cam.full_proj_transform, 3, cam.camera_center, False, False)
-    return ref_ext.GaussianRasterizer(rs)(**kw)
-
-
-def _regularizations(allmap, cam, pipe):
-    out = {"rend_alpha": allmap[1:2], "rend_dist": allmap[6:7],
-           "rend_normal": (allmap[2:5].permute(1, 2, 0) @ cam.world_view_transform[:3, :3].T).permute(2, 0, 1)}
-    out["surf_depth"], out["surf_normal"] = so.surf_depth_normal(allmap, cam, pipe.depth_ratio)
-    return out
-
-
 def _close_grads(ga, gb, name):
     l1 = ((ga - gb).abs().sum() / gb.abs().sum().clamp_min(1e-20)).item()
     out_frac = ((ga - gb).abs() > 1e-2 * gb.abs().max()).float().mean().item()
@@ -238,12 +220,8 @@ def test_render_initial_contract(ref_ext):
     loss_of(out).backward()
 
     pc2 = FakeModel(cloud, None)
-    m2d = torch.zeros_like(pc2.get_xyz, requires_grad=True)
-    _, color, _, radii, allmap = _raster_ref(ref_ext, cam, bg, means3D=pc2.get_xyz, means2D=m2d, opacities=pc2.get_opacity,
-                                             shs=pc2.get_features, features=torch.empty((P, 0)), scales=pc2.get_scaling,
-                                             rotations=pc2.get_rotation)
-    ref = _regularizations(allmap, cam, pipe)
-    ref["render"] = so.linear_to_srgb(color) + bg[:, None, None] * (1 - ref["rend_alpha"])
+    ref = ro.render_initial(ref_ext, cam, pc2, pipe, bg, srgb=True)
+    radii = ref["radii"]
     loss_of(ref).backward()
     assert torch.equal(out["radii"], radii)
     for k in wts:
@@ -286,27 +264,8 @@ def test_render_volume_contract(ref_ext, indirect):
     env.build_mips()
     pc2 = VolumeModel(cloud, env)
     oracle_env = so.EnvLightOracle(list(env.specular), diffuse=env.diffuse)
-    d = pc2.get_xyz - cam.camera_center
-    d = d / d.norm(dim=1, keepdim=True)
-    n = pc2.get_normal(1.0, d)
-    refl_dir = 2 * torch.sum(n * -d, dim=1, keepdim=True) * n + d
-    ind = torch.clamp_min(eval_sh(3, pc2.get_indirect.transpose(1, 2).view(-1, 3, 16), refl_dir), 0.0)
-    diffuse, specular = so.get_full_color_volume(oracle_env, so.load_lut(DEV), pc2.get_xyz, pc2.get_ori_color, cam, n,
-                                                 pc2.get_refl, pc2.get_rough)
-    feats = [pc2.get_rough, pc2.get_refl, diffuse, specular, pc2.get_ori_color]
-    if indirect:   # visibility = 1 without a tracer: specular_light = direct_light (refl_utils.py:460-484)
-        w_o = so.safe_normalize(cam.camera_center.expand(P, -1) - pc2.get_xyz)
-        rr = so.safe_normalize(2 * n * torch.sum(w_o * n, -1, keepdim=True) - w_o)
-        feats += [torch.ones_like(pc2.get_opacity), ind, oracle_env(rr, roughness=pc2.get_rough)]
-    m2d = torch.zeros_like(pc2.get_xyz, requires_grad=True)
-    _, color, feat, radii, allmap = _raster_ref(ref_ext, cam, bg, means3D=pc2.get_xyz, means2D=m2d, opacities=pc2.get_opacity,
-                                                colors_precomp=specular + diffuse, features=torch.cat(feats, -1),
-                                                scales=pc2.get_scaling, rotations=pc2.get_rotation)
-    ref = _regularizations(allmap, cam, pipe)
-    ref.update({"render": color + bg[:, None, None] * (1 - ref["rend_alpha"]), "roughness_map": feat[:1],
-                "refl_strength_map": feat[1:2], "diffuse_map": feat[2:5], "specular_map": feat[5:8], "base_color_map": feat[8:11]})
-    if indirect:
-        ref.update({"visibility": feat[11:12], "indirect_light": feat[12:15], "direct_light": feat[15:18]})
+    ref = ro.render_volume(ref_ext, cam, OracleSide(pc2, oracle_env), pipe, bg, indirect=indirect)
+    radii = ref["radii"]
     loss_of(ref).backward()
 
     assert torch.equal(out["radii"], radii)
