@@ -545,6 +545,9 @@ def main():
     dom = max(("render_fwd", "render_bwd"), key=lambda k: stage_ms[k])
     achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
     line["config"]["R"] = int(R)
+    tiles = ((WORKLOAD["W"] + 15) // 16) * ((WORKLOAD["H"] + 15) // 16)
+    line["config"]["tiles"] = tiles
+    line["config"]["mean_tile_list_length"] = round(int(R) / tiles, 1)
     line["gpu_launches"] = launches
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
     # (profiles/r01_v7_summary.md); only valid for the default C3 workload
