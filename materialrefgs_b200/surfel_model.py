@@ -94,7 +94,7 @@ def save_ply(path, fields: dict) -> None:
         shapes[name] = a.shape[1:]
         if f.transposed:
             a = np.transpose(a, (0, 2, 1))
-        cols.append(a.reshape(P, -1))
+        cols.append(a.reshape(P, int(np.prod(a.shape[1:]))))   # also for an empty cloud (P = 0)
     names = construct_list_of_attributes(shapes)
     table = np.ascontiguousarray(np.concatenate(cols, axis=1), dtype="<f4")
     if table.shape[1] != len(names):
@@ -181,7 +181,8 @@ def load_ply(path, max_sh_degree: int = 3) -> dict:
         out[name] = np.transpose(a.reshape(P, 3, n_rest), (0, 2, 1))
     out["features_dc"] = np.transpose(family("f_dc").reshape(P, 3, 1), (0, 2, 1))
     out["indirect_dc"] = np.transpose(family("ind_dc").reshape(P, 3, 1), (0, 2, 1))
-    out["indirect_asg"] = np.transpose(family("ind_asg").reshape(P, 5, -1), (0, 2, 1))
+    asg = family("ind_asg")
+    out["indirect_asg"] = np.transpose(asg.reshape(P, 5, asg.shape[1] // 5), (0, 2, 1))   # (an empty cloud has no -1 to infer)
     return {k: np.ascontiguousarray(a, dtype=np.float32) for k, a in out.items()}
 
 
@@ -339,7 +340,7 @@ class SurfelStore:
     def densify_and_split(self, grads, grad_threshold, scene_extent, N: int = 2, generator=None):
         n_init = self.num_points
         padded = torch.zeros((n_init,), device=self.device)
-        padded[:grads.shape[0]] = grads.squeeze()
+        padded[:grads.shape[0]] = grads.reshape(-1)
         sel = padded >= grad_threshold
         sel = torch.logical_and(sel, torch.max(self.get_scaling, dim=1).values > self.percent_dense * scene_extent)
         stds = self.get_scaling[sel].repeat(N, 1)
@@ -358,7 +359,7 @@ class SurfelStore:
         grads[grads.isnan()] = 0.0
         self.densify_and_clone(grads, max_grad, extent)
         self.densify_and_split(grads, max_grad, extent, generator=generator)
-        prune = (self.get_opacity < min_opacity).squeeze()
+        prune = (self.get_opacity < min_opacity).squeeze(-1)   # the reference's bare squeeze() breaks at one surfel
         if max_screen_size:
             big_vs = self.max_radii2D > max_screen_size
             big_ws = self.get_scaling.max(dim=1).values > 0.1 * extent

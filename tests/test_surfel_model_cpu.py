@@ -178,3 +178,46 @@ def test_learning_rate_schedule_matches_reference_function():
     assert st.update_learning_rate(30000) == pytest.approx(1.6e-6)
     st.oneupSHdegree(); st.oneupSHdegree(); st.oneupSHdegree(); st.oneupSHdegree()
     assert st.active_sh_degree == 3
+
+
+# ---- invariants over arbitrary densification sequences (hypothesis) ----------------------------------------------
+from hypothesis import given, settings, strategies as st_  # noqa: E402
+
+
+@settings(max_examples=15, deadline=None)
+@given(seed=st_.integers(0, 10_000), P=st_.integers(1, 60), max_grad=st_.floats(1e-5, 5e-3), min_opacity=st_.floats(0.0, 0.6),
+       extent=st_.floats(0.5, 6.0), screen=st_.one_of(st_.none(), st_.integers(1, 40)), rounds=st_.integers(1, 3))
+def test_store_invariants_hold_after_any_densification_sequence(seed, P, max_grad, min_opacity, extent, screen, rounds):
+    """Whatever gets cloned, split or pruned (including everything or nothing): every field, both Adam moments and the three
+    statistics keep one row per surfel, the optimizer still steps, and a .ply round trip returns the same cloud."""
+    g = torch.Generator().manual_seed(seed)
+    fields = random_fields(P, seed)
+    fields["scaling"] = torch.log(0.02 * torch.exp(0.8 * torch.randn((P, 2), generator=g)))
+    store = sm.SurfelStore(fields, lrs={f.group: 1e-3 for f in sm.FIELDS.values()})
+    for _ in range(rounds):
+        n = store.num_points
+        for p in store.params.values():
+            p.grad = 0.01 * torch.randn(p.shape, generator=g)
+        store.optimizer.step()
+        if n:
+            grad = 1e-3 * torch.randn(n, 3, generator=g)
+            radii = (torch.randint(0, 50, (n,), generator=g) * (torch.rand(n, generator=g) > 0.3)).int()
+            store.add_densification_stats(grad, radii > 0, radii)
+        store.densify_and_prune(max_grad, min_opacity, extent, screen, generator=g)
+        n = store.num_points
+        for name, f in sm.FIELDS.items():
+            p = store[name]
+            assert p.shape == (n, *f.shape) and p.requires_grad, name
+            state = store.optimizer.state.get(p)
+            if state:
+                assert state["exp_avg"].shape == p.shape and state["exp_avg_sq"].shape == p.shape, name
+            assert store._group(name)["params"][0] is p
+        assert store.xyz_gradient_accum.shape == (n, 1) and store.denom.shape == (n, 1) and store.max_radii2D.shape == (n,)
+        assert not store.xyz_gradient_accum.any() and not store.max_radii2D.any()      # reset by densification_postfix
+    import tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        path = Path(tmp) / "cloud.ply"
+        store.save_ply(path)
+        back = sm.load_ply(path)
+    for name in sm.FIELDS:
+        assert np.array_equal(back[name], store[name].detach().numpy()), name
