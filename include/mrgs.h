@@ -28,6 +28,17 @@
  *                          EnvLight.get_mip/__call__ scene/light.py:88-129 and the compositing in
  *                          render_surfel gaussian_renderer/__init__.py:419-445
  *   mrgs_cubemap_*      <- scene/renderutils/c_src/cubemap.cu:110-354 + scene/light_utils.py:66-80
+ *   mrgs_envlight_query(_backward) <- EnvLight.__call__ scene/light.py:98-129 (nvdiffrast dr.texture fwd/bwd + sigmoid)
+ *   mrgs_surfel_shade_* <- get_full_color_volume(_indirect) utils/refl_utils.py:426-490 (per-surfel shading of render_volume)
+ *   mrgs_depth_normal_* <- depth_to_normal utils/point_utils.py:9-37 + compute_2dgs_normal_and_regularizations
+ *                          gaussian_renderer/__init__.py:42-90
+ *   mrgs_surfel_features_* <- the activated getters + get_normal + eval_sh of gaussian_renderer/__init__.py:259-353
+ *   mrgs_photometric_*, mrgs_geometry_loss_*, mrgs_img_grad_weight <- calculate_loss / get_img_grad_weight
+ *                          utils/loss_utils.py:22-23, :83-139, :142-228
+ *   mrgs_densify_stats  <- GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061
+ *
+ * ABI history: 5 = gradient sink (accumulate) in mrgs_backward; 6 = mrgs_geometry_loss_*, mrgs_img_grad_weight,
+ * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query.
  */
 #ifndef MRGS_H_INCLUDED
 #define MRGS_H_INCLUDED
@@ -39,7 +50,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 5
+#define MRGS_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))

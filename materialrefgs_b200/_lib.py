@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 5
+MRGS_ABI_VERSION = 6
 MAX_FEATURES = 24
 TILE = 16
 
