@@ -198,6 +198,9 @@ def load() -> C.CDLL:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
+    if lib.mrgs_abi_version() != MRGS_ABI_VERSION:
+        raise ImportError(f"{LIB_PATH} has ABI version {lib.mrgs_abi_version()}, this package needs {MRGS_ABI_VERSION}: "
+                          "rebuild it with `python -m materialrefgs_b200.build --force`")
     _lib = lib
     return lib
 
