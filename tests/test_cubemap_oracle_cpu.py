@@ -51,3 +51,13 @@ def test_shading_oracle_runs_on_cpu_and_is_differentiable():
     lut = so.load_lut()[0]
     assert abs(float(lut[0, 0, 0]) - 0.00972746) < 1e-7 and abs(float(lut[128, 128, 0]) - 0.8342644) < 1e-6
     assert abs(float(lut[255, 0, 1]) - 0.04653827) < 1e-7
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: Path(p).stem)
+def test_product_host_cutoff_search_matches_reference(path):
+    """The host half of specular_cubemap that ships in the product (materialrefgs_b200/cubemap.py, the 10^6-sample search
+    of scene/renderutils/ops.py:428-441) gives the cone angle the reference computed on the GPU box, bit for bit; and
+    EnvLight's roughness schedule (scene/light.py:82-86) is what the product's build_mips uses."""
+    from materialrefgs_b200 import cubemap
+    z = np.load(path)
+    assert cubemap.ndf_cutoff_costheta(float(z["roughness"]), float(z["cutoff"])) == float(z["costheta"])
