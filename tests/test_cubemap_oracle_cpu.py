@@ -56,8 +56,7 @@ def test_shading_oracle_runs_on_cpu_and_is_differentiable():
 @pytest.mark.parametrize("path", GOLDEN, ids=lambda p: Path(p).stem)
 def test_product_host_cutoff_search_matches_reference(path):
     """The host half of specular_cubemap that ships in the product (materialrefgs_b200/cubemap.py, the 10^6-sample search
-    of scene/renderutils/ops.py:428-441) gives the cone angle the reference computed on the GPU box, bit for bit; and
-    EnvLight's roughness schedule (scene/light.py:82-86) is what the product's build_mips uses."""
+    of scene/renderutils/ops.py:428-441) gives the cone angle the reference computed on the GPU box, bit for bit."""
     from materialrefgs_b200 import cubemap
     z = np.load(path)
     assert cubemap.ndf_cutoff_costheta(float(z["roughness"]), float(z["cutoff"])) == float(z["costheta"])
