@@ -30,3 +30,14 @@ def test_oracle_matches_reference_functions(path):
         ref = z["grad_" + k]
         err = np.abs(p[k].grad.numpy() - ref).max() / max(np.abs(ref).max(), 1e-30)
         assert err <= 1e-5, (k, err)
+
+
+def test_product_eval_sh_matches_reference_function():
+    """materialrefgs_b200/render.py eval_sh (host-side torch, used for the indirect light of duck-typed models) against
+    the reference's own utils/sh_utils.py eval_sh at every degree (tests/golden/make_golden_sh.py)."""
+    from materialrefgs_b200 import render
+    z = np.load(Path(__file__).resolve().parent / "golden" / "eval_sh.npz")
+    sh, dirs = torch.from_numpy(z["sh"]), torch.from_numpy(z["dirs"])
+    for deg in range(4):
+        got = render.eval_sh(deg, sh, dirs).numpy()
+        assert np.abs(got - z[f"deg{deg}"]).max() <= 2e-6, deg
