@@ -90,3 +90,51 @@ def test_volume_colours_match_reference_composition():
     for i, l in enumerate(levels):
         ref = z[f"grad_level{i}"]
         assert np.abs(l.grad.numpy() - ref).max() <= 1e-5 * max(np.abs(ref).max(), 1e-12), i
+
+
+# ---- the PRODUCT's host-side matrices (what its kernels are fed) against the reference's own ray / point construction --
+@pytest.mark.parametrize("name", ["surfel_a", "surfel_b"])
+def test_product_ray_matrix_reproduces_reference_camera_rays(name):
+    """materialrefgs_b200.shading.ray_matrix collapses sample_camera_rays (utils/refl_utils.py:54-73, the transposed-R
+    convention, integer pixel centres) into one 3x3: normalising M @ (x, y, 1) must give the reference's rays_d, and
+    _camera_origin its rays_o (vectors from the reference's own function, make_golden_shading.py)."""
+    from materialrefgs_b200 import shading
+    z = np.load(ROOT / "tests" / "golden" / f"shading_{name}.npz")
+    view, W, H, _ = (int(v) for v in z["view"])
+    cam = synthetic.orbit_camera(view, 8, W, H)
+    M = shading.ray_matrix(cam.HWK, cam.R).astype(np.float64)
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    d = np.stack([xs, ys, np.ones_like(xs)], -1) @ M.T
+    d /= np.linalg.norm(d, axis=-1, keepdims=True)
+    assert np.abs(d - z["rays_d"]).max() <= 2e-6
+    assert np.abs(shading._camera_origin(cam.R, cam.T, "cpu").numpy() - z["rays_o"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=lambda p: Path(p).stem)
+def test_product_depth_ray_matrix_reproduces_reference_points(path):
+    """materialrefgs_b200.shading.depth_ray_matrix + the origin surf_depth_normal hands to the kernel: depth * (A @ (x, y, 1))
+    + origin must give the reference's depths_to_points (utils/point_utils.py:9-24, make_golden_depth_normal.py)."""
+    from materialrefgs_b200 import shading
+    z = np.load(path)
+    view, W, H, radius = z["view"]
+    W, H = int(W), int(H)
+    cam = synthetic.orbit_camera(int(view), 8, W, H, radius=float(radius))
+    A = shading.depth_ray_matrix(H, W, cam.tanfovx, cam.tanfovy, cam.R).astype(np.float64)
+    origin = -(np.asarray(cam.R, np.float64) @ np.asarray(cam.T, np.float64))
+    xs, ys = np.meshgrid(np.arange(W, dtype=np.float64), np.arange(H, dtype=np.float64), indexing="xy")
+    rays = np.stack([xs, ys, np.ones_like(xs)], -1).reshape(-1, 3) @ A.T
+    points = z["depth"].reshape(-1, 1) * rays + origin
+    assert np.abs(points - z["points"]).max() <= 2e-5
+
+
+def test_linear_to_srgb_matches_reference_function():
+    """Product (host-side torch) and oracle linear_to_srgb against the reference's utils/graphics_utils.py:102-110,
+    values and derivative, across the branch point and below zero."""
+    from materialrefgs_b200 import shading
+    z = np.load(ROOT / "tests" / "golden" / "linear_to_srgb.npz")
+    for fn in (shading.linear_to_srgb, so.linear_to_srgb):
+        x = torch.from_numpy(z["x"]).requires_grad_(True)
+        y = fn(x)
+        y.sum().backward()
+        assert np.abs(y.detach().numpy() - z["y"]).max() <= 1e-6, fn.__module__
+        assert np.abs(x.grad.numpy() - z["dy"]).max() <= 1e-4 * np.abs(z["dy"]).max(), fn.__module__
