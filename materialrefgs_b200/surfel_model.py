@@ -5,7 +5,7 @@ in order to run an actual loop around the rasterizer:
   * the parameter fields, their shapes and optimizer group names                (:379-410, :422-447)
   * the `.ply` attribute order and per-field transposes                         (:462-523 save_ply, :725-836 load_ply)
   * densification statistics, clone / split / prune, Adam-state surgery         (:856-1061)
-  * reset_opacity0                                                              (:531-534)
+  * reset_opacity0 and the reflection-aware resets the loop chains after it      (:531-545, :558-565, :601-611, :626-671)
   * the checkpoint tuple of capture() / restore() (`chkpnt<iter>.pth`)           (:124-172)
   * the position learning-rate schedule                                         (:455-460, utils/general_utils.py:29-63)
 Pinned by tests/golden/densify_*.npz, produced by the reference's own methods (tests/golden/make_golden_densify.py).
@@ -232,6 +232,11 @@ _CAPTURE_ORDER = ("xyz", "refl_strength", "metalness", "roughness", "ori_color",
 class SurfelStore:
     """Parameters, Adam optimizer and densification statistics of a surfel cloud (GaussianModel's bookkeeping)."""
     max_sh_degree = 3
+    # thresholds of the reflection-aware resets (gaussian_model.py:106-112; train_refnerf.py:1510 sets enlarge_scale)
+    init_refl_value = 0.1
+    enlarge_scale = 1.5
+    refl_msk_thr = 0.02
+    rough_msk_thr = 0.1
 
     def __init__(self, fields: dict, lrs: dict | None = None, percent_dense: float = 0.01, frozen=("normal1", "normal2"),
                  spatial_lr_scale: float = 1.0, active_sh_degree: int = 0, xyz_schedule: dict | None = None):
@@ -370,6 +375,61 @@ class SurfelStore:
         """:531-534."""
         new = inverse_sigmoid(torch.min(self.get_opacity, torch.ones_like(self.get_opacity) * 0.01)).detach()
         self.replace_tensor_to_optimizer("opacity", new)
+
+    # -- the resets the training loop applies after an opacity reset (train_refnerf.py:1439-1455)
+    @property
+    def get_refl(self):
+        return torch.sigmoid(self.params["refl_strength"])
+
+    @property
+    def get_rough(self):
+        return torch.sigmoid(self.params["roughness"])
+
+    def reset_opacity1(self, exclusive_msk=None):
+        """:536-545 — opacities above 0.9 (or excluded) keep their value, the rest restart at 0.9."""
+        RESET_V = 0.9
+        opacity_old = self.get_opacity
+        o_msk = (opacity_old > RESET_V).flatten()
+        if exclusive_msk is not None:
+            o_msk = torch.logical_or(o_msk, exclusive_msk)
+        new = torch.ones_like(opacity_old) * inverse_sigmoid(torch.tensor([RESET_V], device=self.device))
+        new[o_msk] = self.params["opacity"].detach()[o_msk]
+        self.replace_tensor_to_optimizer("opacity", new.detach())
+
+    def reset_refl(self, exclusive_msk=None, rst_value=None):
+        """:558-565 — the reflection strength is raised to at least rst_value (excluded surfels keep theirs)."""
+        rst_value = self.init_refl_value if rst_value is None else rst_value
+        new = inverse_sigmoid(torch.max(self.get_refl, torch.ones_like(self.get_refl) * rst_value)).detach()
+        if exclusive_msk is not None:
+            new[exclusive_msk] = self.params["refl_strength"].detach()[exclusive_msk]
+        self.replace_tensor_to_optimizer("refl_strength", new)
+
+    def dist_color(self, exclusive_msk=None):
+        """:601-611 — the DC colour of NON-reflective surfels is perturbed by U(-0.4, 0.4) (global torch RNG)."""
+        DIST_RANGE = 0.4
+        refl_msk = self.get_refl.flatten() > self.refl_msk_thr
+        if exclusive_msk is not None:
+            refl_msk = torch.logical_or(refl_msk, exclusive_msk)
+        dcc = self.params["features_dc"].detach().clone()
+        dist = dcc + (torch.rand_like(dcc) * DIST_RANGE * 2 - DIST_RANGE)
+        dist[refl_msk] = dcc[refl_msk]
+        self.replace_tensor_to_optimizer("features_dc", dist)
+
+    def enlarge_refl_scales(self, exclusive_msk=None):
+        """:626-645 (ret_raw=True) — reflective, smooth surfels grow by enlarge_scale; the others keep their raw scale."""
+        refl_msk = self.get_refl.flatten() < self.refl_msk_thr
+        rough_msk = self.get_rough.flatten() > self.rough_msk_thr
+        combined = torch.logical_or(refl_msk, rough_msk)
+        if exclusive_msk is not None:
+            combined = torch.logical_or(combined, exclusive_msk)
+        scales = self.get_scaling
+        new = torch.log(scales * (torch.ones_like(scales) * self.enlarge_scale)).detach()
+        new[combined] = self.params["scaling"].detach()[combined]
+        return new
+
+    def reset_scale(self, exclusive_msk=None):
+        """:667-671."""
+        self.replace_tensor_to_optimizer("scaling", self.enlarge_refl_scales(exclusive_msk=exclusive_msk))
 
     # -- schedule (gaussian_model.py:455-460, :311-313)
     def update_learning_rate(self, iteration):

@@ -64,6 +64,7 @@ sys.modules["utils.refl_utils"] = _Stub("utils.refl_utils")
 sys.modules["raytracing_brdf"] = _Stub("raytracing_brdf")     # same at raytracing_brdf/raytracer.py:13
 _zeros = torch.zeros
 torch.zeros = lambda *a, **kw: _zeros(*a, **{k: v for k, v in kw.items() if k != "device"})
+torch.Tensor.cuda = lambda self, *a, **k: self      # reset_opacity1 builds its constant with .cuda() (:541)
 
 from scene.gaussian_model import GaussianModel  # noqa: E402  (the reference's)
 from utils.general_utils import inverse_sigmoid  # noqa: E402
@@ -194,6 +195,38 @@ def checkpoint_and_schedule():
     print("wrote chkpnt_reference_small.pth, lr_schedule.npz")
 
 
+def resets():
+    """reset_opacity1 / reset_refl / dist_color / reset_scale as the training loop chains them after an opacity reset
+    (train_refnerf.py:1439-1455), with and without an exclusion mask."""
+    P, seed = 150, 12
+    m, args = make_reference_model(initial_fields(P, seed), 0.01)
+    m.init_refl_value, m.enlarge_scale, m.refl_msk_thr, m.rough_msk_thr = 0.1, 1.5, 0.02, 0.1
+    m.refl_activation = m.roughness_activation = torch.sigmoid
+    m.inverse_refl_activation = inverse_sigmoid
+    with torch.no_grad():     # spread the material parameters over both sides of the thresholds
+        g = torch.Generator().manual_seed(seed + 5)
+        m._refl_strength.copy_(torch.randn(P, 1, generator=g) * 3 - 3)
+        m._roughness.copy_(torch.randn(P, 1, generator=g) * 2 - 2)
+        m._opacity.copy_(torch.randn(P, 1, generator=g) * 3 + 1)
+    adam_warmup([getattr(m, a) for a in FIELDS], m.optimizer, 2, seed + 1)
+    out = {"P": P, "seed": seed}
+    out.update({"before_" + k: v for k, v in snapshot(m).items()})
+    msk = torch.rand(P, generator=torch.Generator().manual_seed(seed + 6)) < 0.3
+    out["mask"] = msk.numpy()
+    for tag, mask in (("plain", None), ("masked", msk)):
+        m.reset_opacity0()
+        m.reset_refl(exclusive_msk=mask, rst_value=0.1 if mask is not None else None)
+        m.reset_opacity1(exclusive_msk=mask)
+        torch.manual_seed(seed + 7)
+        m.dist_color(exclusive_msk=mask)
+        m.reset_scale(exclusive_msk=mask)
+        out.update({f"{tag}_" + k: v for k, v in snapshot(m).items()
+                    if k[:2] in ("p_", "m_", "v_") and k[2:] in ("opacity", "refl_strength", "f_dc", "scaling")})
+    np.savez_compressed(ROOT / "tests" / "golden" / "resets.npz", **out)
+    print("wrote resets.npz")
+
+
 if __name__ == "__main__":
     main()
     checkpoint_and_schedule()
+    resets()

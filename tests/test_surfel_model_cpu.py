@@ -221,3 +221,33 @@ def test_store_invariants_hold_after_any_densification_sequence(seed, P, max_gra
         back = sm.load_ply(path)
     for name in sm.FIELDS:
         assert np.array_equal(back[name], store[name].detach().numpy()), name
+
+
+def test_reflection_aware_resets_match_reference_methods():
+    """reset_opacity0 -> reset_refl -> reset_opacity1 -> dist_color -> reset_scale as train_refnerf.py:1439-1455 chains
+    them, without and with an exclusion mask, against the reference's own methods (tests/golden/resets.npz): parameters
+    bit-equal, Adam moments zeroed the same way."""
+    z = np.load(ROOT / "tests" / "golden" / "resets.npz")
+    st = store_from_golden(_with_percent_dense(z))
+    msk = torch.from_numpy(z["mask"])
+    for tag, mask in (("plain", None), ("masked", msk)):
+        st.reset_opacity0()
+        st.reset_refl(exclusive_msk=mask, rst_value=0.1 if mask is not None else None)
+        st.reset_opacity1(exclusive_msk=mask)
+        torch.manual_seed(int(z["seed"]) + 7)
+        st.dist_color(exclusive_msk=mask)
+        st.reset_scale(exclusive_msk=mask)
+        for name, group in (("opacity", "opacity"), ("refl_strength", "refl_strength"), ("features_dc", "f_dc"), ("scaling", "scaling")):
+            assert np.array_equal(st[name].detach().numpy(), z[f"{tag}_p_{group}"]), (tag, name)
+            state = st.optimizer.state[st[name]]
+            assert np.array_equal(state["exp_avg"].numpy(), z[f"{tag}_m_{group}"]), (tag, name)
+            assert np.array_equal(state["exp_avg_sq"].numpy(), z[f"{tag}_v_{group}"]), (tag, name)
+
+
+class _with_percent_dense:
+    """An npz view that also answers `percent_dense` (store_from_golden reads it from the densify vectors)."""
+    def __init__(self, z):
+        self.z, self.files = z, list(z.files) + ["percent_dense"]
+
+    def __getitem__(self, k):
+        return np.float64(0.01) if k == "percent_dense" else self.z[k]
