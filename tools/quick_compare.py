@@ -1,7 +1,6 @@
 """Ad-hoc timing of reference (oracle/_ref) vs libmrgs on one synthetic view. Dev tool only."""
 import argparse
 import sys
-import time
 from pathlib import Path
 
 import torch
