@@ -1,21 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — 800x800 forward+backward frames/s of the full MaterialRefGS render path
-(rasterize + material G-buffer + fused deferred PBR shading) on synthetic random-init surfels.
+"""bench.py — 800x800 forward+backward frames/s of the full MaterialRefGS render path on synthetic surfels.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config C3|C5|C5-eval|C2|C4]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one training step of a rank: VIEWS_PER_RANK (4) views of config C3 of BASELINE.json (1 M
-surfels, 800x800, S = 8 material channels, SH degree 3, 6x512^2 logit cubemap with 6 mip levels)
-rendered forward+backward with gradient accumulation. With N > 1 every rank renders different views of
-the same replicated cloud and ONE NCCL allreduce per step sums the per-surfel gradient arena +
-densification statistics (weak scaling: per-GPU work fixed; value = N * 4 views / step time).
+Default workload = BASELINE.json configs[2] ("C3"): 1 M surfels, 800x800, S = 8 material channels, SH degree 3,
+trainable 6x512^2 logit cubemap with 6 GGX mip levels. One "step" = one training step of a rank, run the way the
+reference runs an iteration (train_refnerf.py:1155-1173) but over a batch of views:
+    EnvLight.build_mips()                                   (scene/light.py:72-86, every iteration in the reference)
+    VIEWS_PER_RANK x [ rasterize -> G-buffer -> fused deferred PBR shading -> loss -> backward ]
+    (N > 1) ONE sum-allreduce of [per-surfel gradient arena | densification statistics | cubemap texel-gradient sink]
+    build_mips backward: texel-gradient sink -> base cubemap gradient
+With N > 1 every rank renders different views of the same replicated cloud (weak scaling for C3: per-GPU work fixed,
+value = N * views / step time; C5 fixes the batch at 8 views = strong scaling; C5-eval shards 200 cameras, no collective).
 
-Prints ONE JSON line (see the driver contract in the task description). `--impl reference` runs the
-unmodified reference CUDA rasterizer from oracle/_ref through its own Python API on the same GPU
-(the reference has no CPU rasterizer, BASELINE.json north_star) plus the eager-torch restatement of
-its shading (nvdiffrast is not available), or — when oracle/_ref is missing — the CPU oracle port
-on a bounded tile sample.
+Prints ONE JSON line (driver contract). `--impl reference` times the UNMODIFIED reference code on the same GPU: its CUDA
+rasterizer (oracle/_ref/diff_surfel_rasterization) through its own Python API, plus build_mips forward+backward through
+its own renderutils plugin ops (oracle/_ref/renderutils_plugin). The reference has no CPU rasterizer (BASELINE.json
+north_star); its nvdiffrast shading cannot run here (un-vendored dependency), so that arm does LESS work than ours.
+The reference arm imports nothing of the product (no libmrgs.so in its process).
 """
 from __future__ import annotations
 
@@ -34,13 +37,33 @@ sys.path.insert(0, str(ROOT))
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
-WORKLOAD = dict(P=1_000_000, S=8, W=800, H=800, sh_degree=3, cube_res=512, min_res=16, opacity="trained")
-METRIC = "800x800 frames/s fwd+bwd at 1M surfels (rasterize + G-buffer + deferred PBR shading)"
-VIEWS_PER_RANK = 4   # views rendered per rank per step (gradient accumulation) before the single allreduce
+BASE = dict(S=8, W=800, H=800, sh_degree=3, cube_res=512, min_res=16, opacity="trained", unbounded=False, radius=4.0,
+            shade=True, mode="train", scaling="weak", views_per_rank=4, batch_views=None)
+WORKLOADS = {
+    "C3": dict(BASE, P=1_000_000,
+               metric="800x800 frames/s fwd+bwd at 1M surfels (build_mips + rasterize + G-buffer + deferred PBR shading)",
+               text="C3: 1M random-init surfels (trained-like opacity), 800x800, S=8 material channels, SH degree 3, "
+                    "EnvLight.build_mips fwd+bwd every step (trainable 6x512^2 cubemap, 6 mips) + per view rasterize + fused "
+                    "deferred PBR shading, fwd+bwd"),
+    "C5": dict(BASE, P=5_000_000, scaling="strong", batch_views=8,
+               metric="800x800 frames/s fwd+bwd at 5M surfels, 8-view batch training step",
+               text="C5: 5M surfels, 800x800, 8-view batch per step split over the ranks (strong scaling), build_mips + "
+                    "rasterize + shading fwd+bwd, one allreduce per step"),
+    "C5-eval": dict(BASE, P=5_000_000, scaling="strong", mode="eval", batch_views=200,
+                    metric="800x800 eval frames/s at 5M surfels, 200 cameras sharded by camera",
+                    text="C5-eval: 5M surfels, 200-view evaluation render (forward only, no_grad) sharded by camera, no collective"),
+    "C2": dict(BASE, P=300_000, opacity="init", shade=False, views_per_rank=1,
+               metric="800x800 frames/s rasterize fwd+bwd at 300k surfels",
+               text="C2: 300k random-init surfels (opacity 0.1), single 800x800 view, surfel rasterize fwd+bwd only"),
+    "C4": dict(BASE, P=3_000_000, W=1920, H=1080, unbounded=True, radius=3.0, views_per_rank=2,
+               metric="1920x1080 frames/s fwd+bwd at 3M surfels",
+               text="C4: 3M surfels, unbounded Ref-Real-like cloud, 1920x1080, build_mips + rasterize + shading fwd+bwd"),
+}
+N_CAMS = 8
 
 
 # ------------------------------------------------------------------------------------------------
-def dist_setup(n_gpus: int):
+def dist_setup():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -50,7 +73,7 @@ def dist_setup(n_gpus: int):
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
-        torch.cuda.set_device(0)
+        torch.cuda.set_device(local)
     return rank, local, world
 
 
@@ -71,6 +94,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.gpu = gpu_index
         self.p = None
+        self.skip = 0
 
     def start(self):
         try:
@@ -97,7 +121,7 @@ class ClockSampler:
         except Exception:
             self.p.kill()
         self.f.flush()
-        lines = Path(self.f.name).read_text().strip().splitlines()[getattr(self, "skip", 0):]
+        lines = Path(self.f.name).read_text().strip().splitlines()[self.skip:]
         rows = [r.split(",") for r in lines if r.count(",") >= 8]
         os.unlink(self.f.name)
         if not rows:
@@ -119,155 +143,94 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
+def balanced_assignment(costs, world, per_rank):
+    """Longest-processing-time-first assignment of len(costs) = world * per_rank items to ranks with exactly
+    per_rank items each; returns a list of item-index lists. Deterministic, identical on every rank."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    load, out = [0.0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min((r for r in range(world) if len(out[r]) < per_rank), key=lambda r: (load[r], r))
+        out[r].append(i)
+        load[r] += costs[i]
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
-def make_scene(dev, rank):
-    from materialrefgs_b200 import synthetic
-    w = WORKLOAD
-    cloud = synthetic.make_cloud(w["P"], S=w["S"], opacity=w["opacity"]).to(dev)
-    cams = [synthetic.orbit_camera(i, 8, w["W"], w["H"]) for i in range(8)]
-    rng = np.random.RandomState(99)
-    N = w["H"] * w["W"]
-    up = {k: torch.from_numpy((rng.normal(size=(c, w["H"], w["W"])) / N).astype(np.float32))
-          for k, c in (("render", 3), ("allmap", 7), ("normal", 3))}
-    return cloud, cams, up
+class StepBase:
+    """Scene, view schedule and the end-to-end plumbing (pinned host buffers, one copy stream, double-buffered device
+    inputs). Plain torch + the synthetic generators only: both arms build on it, neither arm's code is in it."""
+    name = "base"
 
-
-def build_chain(dev, impl):
-    """6x512^2 logit cubemap ~ N(0,1) and its GGX-prefiltered mip chain (built once, outside the
-    timed region; EnvLight.build_mips is a separate call in the reference's training loop)."""
-    w = WORKLOAD
-    g = torch.Generator().manual_seed(1234)
-    base = torch.randn(6, w["cube_res"], w["cube_res"], 3, generator=g).to(dev)
-    from materialrefgs_b200.shading import EnvLight
-    env = EnvLight(device=dev, max_res=w["cube_res"], min_res=w["min_res"], trainable=False)
-    with torch.no_grad():
-        env.base.copy_(base)
-        env.build_mips()
-    return [l.detach().clone().contiguous() for l in env.specular], env
-
-
-class OursStep:
-    name = "ours"
-
-    def __init__(self, dev, rank, world):
-        from materialrefgs_b200 import _lib
-        from materialrefgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
-        from materialrefgs_b200.shading import shade_surfel
-        self.lib = _lib.load()
-        self._lib = _lib
-        self.dev, self.rank, self.world = dev, rank, world
-        self.cloud, self.cams, up = make_scene(dev, rank)
-        self.up_host = {k: v.pin_memory() for k, v in up.items()}
-        self.up = {k: v.to(dev) for k, v in up.items()}
-        levels, self.env = build_chain(dev, "ours")
-        self.levels = [l.requires_grad_(True) for l in levels]
-        self.env.set_chain(self.levels)
+    def __init__(self, dev, rank, world, wl):
+        from materialrefgs_b200 import synthetic   # numpy/torch generators, does not load libmrgs.so
+        self.dev, self.rank, self.world, self.wl = dev, rank, world, wl
+        self.cloud = synthetic.make_cloud(wl["P"], S=wl["S"], opacity=wl["opacity"], unbounded=wl["unbounded"]).to(dev)
+        self.cams = [synthetic.orbit_camera(i, N_CAMS, wl["W"], wl["H"], radius=wl["radius"]) for i in range(N_CAMS)]
+        rng = np.random.RandomState(99)
+        N = wl["H"] * wl["W"]
+        up = {k: torch.from_numpy((rng.normal(size=(c, wl["H"], wl["W"])) / N).astype(np.float32))
+              for k, c in (("render", 3), ("allmap", 7), ("normal", 3), ("feature", wl["S"]))}
+        self.up_host = {k: v.pin_memory() for k, v in up.items() if k in self.upstream_keys()}
+        self.up = {k: v.to(dev) for k, v in self.up_host.items()}
         self.leaves = {k: getattr(self.cloud, k).clone().requires_grad_(True)
                        for k in ("means3D", "scales", "rotations", "opacities", "shs", "features")}
         self.means2D = torch.zeros_like(self.leaves["means3D"], requires_grad=True)
         self.bg = torch.zeros(3, device=dev)
-        self.GRS, self.GR, self.shade = GaussianRasterizationSettings, GaussianRasterizer, shade_surfel
         self.cam_dev = [c.to(dev) for c in self.cams]
         self.cam_host = [(c.world_view_transform.pin_memory(), c.full_proj_transform.pin_memory(),
                           c.camera_center.pin_memory()) for c in self.cams]
-        # The gradient arena (materialrefgs_b200/parallel.py) is the parameters' .grad AND the rasterizer's
-        # grad_sink: the per-surfel backward adds every view's gradients into it, one allreduce follows (N > 1).
-        from materialrefgs_b200.parallel import GradArena
-        self.arena = GradArena.create(WORKLOAD["P"], dev)
-        self.arena.bind(self.leaves)
-        self.sink = self.arena.views if self.name == "ours" else None
-        # texel gradients of the mip chain: summed over the step's views in one persistent buffer (shading.py)
-        self.level_sink = self.env.enable_level_grad_sink() if self.name == "ours" else None
+        g = torch.Generator().manual_seed(1234)
+        self.base_init = torch.randn(6, wl["cube_res"], wl["cube_res"], 3, generator=g)
+        self.train = wl["mode"] == "train"
+        if wl["batch_views"] is None:
+            self.V = wl["views_per_rank"]
+        else:
+            self.V = len(range(rank, wl["batch_views"], world))
+        self.total_views = wl["views_per_rank"] * world if wl["batch_views"] is None else wl["batch_views"]
+        self.cost = [1.0] * N_CAMS       # per-camera cost (instances R of the last render), identical on all ranks
         self.last = {}
 
-    def zero_grads(self):
-        self.arena.zero_()                 # one memset: gradient segments + statistics tail
-        for t in self.levels + [self.means2D]:
-            t.grad = None
+    def upstream_keys(self):
+        return ("render", "allmap", "normal")
 
-    def render(self, view, cam_mats, up):
-        cam = self.cams[view]
-        wvt, proj, center = cam_mats
-        rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, wvt, proj,
-                      WORKLOAD["sh_degree"], center, False, False)
-        L = self.leaves
-        contrib, color, feat, radii, allmap = (self.GR(rs, grad_sink=self.sink) if self.sink is not None else self.GR(rs))(
-            means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
-            features=L["features"], scales=L["scales"], rotations=L["rotations"])
-        out = self.shade(self.env, color, feat, allmap, cam.HWK, cam.R, self.bg)
-        loss = (out["render"] * up["render"]).sum() + (allmap * up["allmap"]).sum() + \
-               (out["rend_normal"] * up["normal"]).sum()
-        loss.backward()
-        self.last = {"radii": radii, "render": out["render"], "loss": loss}
-        return loss
+    # ---- view schedule ---------------------------------------------------------------------------------
+    def views_for_step(self, i):
+        """Camera indices this rank renders in step i. The step's views are dealt to the ranks by cost (instances of the
+        camera's last render) so that no rank waits for the slowest: LPT with equal counts."""
+        T, W = self.total_views, self.world
+        cams = [(i * T + k + i) % N_CAMS for k in range(T)]        # + i: every rank cycles through all cameras
+        if W == 1:
+            return cams
+        if T % W == 0:
+            parts = balanced_assignment([self.cost[c] for c in cams], W, T // W)
+            return [cams[k] for k in parts[self.rank]]
+        return cams[self.rank::W]
 
-    def step(self, i, e2e=False):
-        """One training step of this rank: VIEWS_PER_RANK views rendered forward+backward with gradient
-        accumulation (autograd sums into .grad = the arena segments), then — when sharded — ONE allreduce of the flat
-        gradient arena + densification statistics (materialrefgs_b200/parallel.py)."""
-        self.zero_grads()
-        V = VIEWS_PER_RANK
-        total = 0.0
-        view_at = lambda step, v: ((step * V + v) * self.world + self.rank + step) % len(self.cams)   # + step: every rank cycles through all cameras
-        view_of = lambda v: view_at(i, v)
-        if e2e and getattr(self, "prefetched_step", None) != i:
-            self._e2e_prefetch(view_of(0))
-        for v in range(V):
-            view = view_of(v)
-            if e2e:  # host -> device: camera + upstream-gradient maps (per-view inputs); surfels are model state
-                cam_mats, up = self._e2e_take()
-                if v + 1 < V:
-                    self._e2e_prefetch(view_of(v + 1))   # next view's H2D overlaps this view's kernels
-                else:                                    # like a data loader: the next step's first view is in flight
-                    self._e2e_prefetch(view_at(i + 1, 0))
-                    self.prefetched_step = i + 1
-            else:
-                c = self.cam_dev[view]
-                cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
-            self.means2D.grad = None   # the densification norm is taken per view (gaussian_model.py:1059-1061)
-            loss = self.render(view, cam_mats, up)
-            if self.world > 1:
-                self.arena.accumulate_view({}, self.means2D.grad, self.last["radii"])
-            if e2e:  # device -> host: the rendered image and the loss of every view (copy stream, pinned target)
-                self._e2e_readback(i & 1, v, loss)
-        if e2e:
-            # results are consumed like a training loop logs them: step i's copies are in flight while step i+1 is
-            # enqueued; the host waits for (and reads) the PREVIOUS step's image + losses here, the last step's in
-            # e2e_finish() — every step's result is read inside the timed region, the pipeline never drains
-            self.result_events[i & 1].record(self.copy_stream)
-            total = self._e2e_consume((i & 1) ^ 1)
-            self.result_pending[i & 1] = True
-        if self.world > 1:                 # autograd accumulated in place: no flattening copy
-            self.arena.allreduce(extra=(self.level_sink,) if self.level_sink is not None else ())
-        if self.level_sink is not None:
-            self.env.flush_level_grads()   # the (all-reduced) chain gradient reaches the levels' .grad once per step
-        return total if e2e else None
-
-    # ---- end-to-end plumbing: pinned host buffers, one copy stream, double-buffered device inputs ----------
+    # ---- end-to-end plumbing ------------------------------------------------------------------------------
     def _e2e_init(self):
         if hasattr(self, "copy_stream"):
             return
+        V = max(self.V, 1)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.in_slots = [None, None]
         self.in_events = [torch.cuda.Event(), torch.cuda.Event()]
         self.free_events = [None, None]
         self.slot = 0
         # two sets of pinned result buffers (step parity): one is read by the host while the other is being filled
-        self.img_host = [[torch.empty((3, WORKLOAD["H"], WORKLOAD["W"]), dtype=torch.float32).pin_memory()
-                          for _ in range(VIEWS_PER_RANK)] for _ in range(2)]
-        self.loss_host = [torch.empty(VIEWS_PER_RANK, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.img_host = [[torch.empty((3, self.wl["H"], self.wl["W"]), dtype=torch.float32).pin_memory()
+                          for _ in range(V)] for _ in range(2)]
+        self.loss_host = [torch.empty(V, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.result_events = [torch.cuda.Event(), torch.cuda.Event()]
         self.result_pending = [False, False]
 
     def _e2e_prefetch(self, view):
         self._e2e_init()
         k = self.slot
-        main = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(self.copy_stream):
             if self.free_events[k] is not None:
                 self.copy_stream.wait_event(self.free_events[k])   # the slot's previous consumer has finished
             cam = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
-            up = {n: t.to(self.dev, non_blocking=True) for n, t in self.up_host.items()}
+            up = {n: t.to(self.dev, non_blocking=True) for n, t in self.up_host.items()} if self.train else {}
             self.in_events[k].record(self.copy_stream)
         self.in_slots[k] = (cam, up)
         self.pending = k
@@ -288,7 +251,8 @@ class OursStep:
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(done)
             self.img_host[par][v].copy_(img, non_blocking=True)
-            self.loss_host[par][v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            if loss is not None:
+                self.loss_host[par][v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         img.record_stream(self.copy_stream)
 
     def _e2e_consume(self, par):
@@ -297,48 +261,241 @@ class OursStep:
             return 0.0
         self.result_events[par].synchronize()
         self.result_pending[par] = False
-        return float(sum(float(self.loss_host[par][v]) + float(self.img_host[par][v][0, 0, 0])
-                         for v in range(VIEWS_PER_RANK)))
+        return float(sum(float(self.loss_host[par][v]) + float(self.img_host[par][v][0, 0, 0]) for v in range(self.V)))
 
     def e2e_finish(self):
         return self._e2e_consume(0) + self._e2e_consume(1)
 
     def h2d_bytes(self):
-        return VIEWS_PER_RANK * (sum(v.numel() * 4 for v in self.up_host.values()) + (16 + 16 + 3) * 4)
+        per_view = (16 + 16 + 3) * 4 + (sum(v.numel() * 4 for v in self.up_host.values()) if self.train else 0)
+        return self.V * per_view
 
     def d2h_bytes(self):
-        return VIEWS_PER_RANK * (3 * WORKLOAD["H"] * WORKLOAD["W"] * 4 + 4)
+        return self.V * (3 * self.wl["H"] * self.wl["W"] * 4 + (4 if self.train else 0))
 
+    # ---- one step ---------------------------------------------------------------------------------------
+    def begin_step(self):
+        pass
 
-class ReferenceStep(OursStep):
-    """The unmodified reference rasterizer (oracle/_ref) through its own Python API on the same GPU.
-    Its shading cannot run here (nvdiffrast is an un-vendored dependency), so this arm does LESS work
-    than ours: rasterize forward+backward only, with upstream gradients on every output."""
-    name = "reference"
-
-    def __init__(self, dev, rank, world):
-        super().__init__(dev, rank, world)
-        from tests import refimpl
-        ref = refimpl.load_reference()
-        if ref is None:
-            raise RuntimeError("oracle/_ref is not available")
-        self.GRS, self.GR = ref.GaussianRasterizationSettings, ref.GaussianRasterizer
-        rng = np.random.RandomState(7)
-        N = WORKLOAD["H"] * WORKLOAD["W"]
-        self.up_feat = torch.from_numpy((rng.normal(size=(WORKLOAD["S"], WORKLOAD["H"], WORKLOAD["W"])) / N)
-                                        .astype(np.float32)).to(dev)
+    def end_step(self):
+        pass
 
     def render(self, view, cam_mats, up):
+        raise NotImplementedError
+
+    def step(self, i, e2e=False):
+        views = self.views_for_step(i)
+        self.begin_step()
+        if e2e and views and getattr(self, "prefetched_step", None) != i:
+            self._e2e_prefetch(views[0])
+        for v, view in enumerate(views):
+            if e2e:  # host -> device: camera + upstream-gradient maps (per-view inputs); surfels are model state
+                cam_mats, up = self._e2e_take()
+                if v + 1 < len(views):
+                    self._e2e_prefetch(views[v + 1])   # next view's H2D overlaps this view's kernels
+                else:                                  # like a data loader: the next step's first view is in flight
+                    nxt = self.views_for_step(i + 1)
+                    if nxt:
+                        self._e2e_prefetch(nxt[0])
+                        self.prefetched_step = i + 1
+            else:
+                c = self.cam_dev[view]
+                cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
+            loss = self.render(view, cam_mats, up, last=(v == len(views) - 1))
+            if e2e:  # device -> host: the rendered image and the loss of every view (copy stream, pinned target)
+                self._e2e_readback(i & 1, v, loss)
+        total = None
+        if e2e:
+            # results are consumed like a training loop logs them: step i's copies are in flight while step i+1 is
+            # enqueued; the host waits for (and reads) the PREVIOUS step's image + losses here, the last step's in
+            # e2e_finish() — every step's result is read inside the timed region, the pipeline never drains
+            self.result_events[i & 1].record(self.copy_stream)
+            total = self._e2e_consume((i & 1) ^ 1)
+            self.result_pending[i & 1] = True
+        self.end_step()
+        return total
+
+
+class OursStep(StepBase):
+    name = "ours"
+
+    def __init__(self, dev, rank, world, wl):
+        super().__init__(dev, rank, world, wl)
+        from materialrefgs_b200 import _lib
+        from materialrefgs_b200.diff_surfel_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        from materialrefgs_b200.parallel import GradArena
+        from materialrefgs_b200.shading import EnvLight, shade_surfel
+        self._lib, self.lib = _lib, _lib.load()
+        self.GRS, self.GR, self.shade = GaussianRasterizationSettings, GaussianRasterizer, shade_surfel
+        self.env = None
+        texels = 0
+        if wl["shade"]:
+            self.env = EnvLight(device=dev, max_res=wl["cube_res"], min_res=wl["min_res"], trainable=self.train)
+            with torch.no_grad():
+                self.env.base.copy_(self.base_init.to(dev))
+            self.env.build_mips()
+            texels = sum(l.shape[0] * l.shape[1] * l.shape[2] for l in self.env.specular)
+        # ONE flat buffer: [parameter gradients | densification statistics | cubemap texel-gradient sink]; the segments
+        # are the parameters' .grad AND the rasterizer's grad_sink, the tail is EnvLight's level-gradient sink: every
+        # producer kernel writes straight into the buffer that is all-reduced (materialrefgs_b200/parallel.py)
+        self.arena = GradArena.create(wl["P"], dev, extra_floats=4 * texels if self.train else 0)
+        self.sink = None
+        if self.train:
+            self.arena.bind(self.leaves)
+            self.sink = self.arena.views
+            if self.env is not None:
+                self.env.use_level_grad_sink(self.arena.extra.view(texels, 4))
+
+    def begin_step(self):
+        if self.train:
+            self.arena.zero_()                 # one memset: gradients + statistics (+ the sink, zero after its flush)
+            self.means2D.grad = None
+            if self.env is not None:
+                self.env.base.grad = None
+        if self.env is not None and self.train:
+            self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
+
+    def render(self, view, cam_mats, up, last=False):
+        cam = self.cams[view]
+        wvt, proj, center = cam_mats
+        wl = self.wl
+        rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, wvt, proj,
+                      wl["sh_degree"], center, False, False)
+        L = self.leaves
+        rast = self.GR(rs, grad_sink=self.sink) if self.sink is not None else self.GR(rs)
+        with torch.set_grad_enabled(self.train):
+            contrib, color, feat, radii, allmap = rast(
+                means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
+                features=L["features"], scales=L["scales"], rotations=L["rotations"])
+            self.cost[view] = float(rast.num_rendered) if getattr(rast, "num_rendered", None) else self.cost[view]
+            if self.env is not None:
+                out = self.shade(self.env, color, feat, allmap, cam.HWK, cam.R, self.bg)
+                image, normal = out["render"], out["rend_normal"]
+            else:
+                image, normal = color, None
+            loss = None
+            if self.train:
+                self.means2D.grad = None   # the densification norm is taken per view (gaussian_model.py:1059-1061)
+                loss = (image * up["render"]).sum() + (allmap * up["allmap"]).sum()
+                if normal is not None:
+                    loss = loss + (normal * up["normal"]).sum()
+                if last and self.world > 1 and self.env is not None:
+                    self.env.after_sink_backward = self._sink_ready   # fires right after the last shading backward
+                loss.backward()
+                if self.world > 1:
+                    self.arena.accumulate_view({}, self.means2D.grad, radii)
+        self.last = {"radii": radii, "render": image, "loss": loss}
+        return loss
+
+    def _sink_ready(self):
+        """The cubemap texel gradients of this rank are complete once the LAST view's shading backward is enqueued: their
+        allreduce starts now, under the rasterizer backward of that view (NCCL stream, waits for the work enqueued so far)."""
+        self.env.after_sink_backward = None
+        self.sink_work = self.arena.allreduce_extra_async()
+
+    def end_step(self):
+        if not self.train:
+            return
+        if self.world > 1:
+            # arena allreduce (272 MB at 1 M surfels) on NCCL's stream WHILE the main stream runs the build_mips backward,
+            # which only needs the texel-gradient sink (reduced above, under the last view's rasterizer backward)
+            work = self.arena.allreduce_main_async()
+            if self.env is not None:
+                if getattr(self, "sink_work", None) is not None:
+                    self.sink_work.wait()
+                    self.sink_work = None
+                self.env.flush_level_grads()
+            self.arena.wait(work)
+        elif self.env is not None:
+            self.env.flush_level_grads()
+
+
+class ReferenceStep(StepBase):
+    """The UNMODIFIED reference code on the same GPU, nothing of the product loaded: its CUDA rasterizer through its own
+    Python API (rasterize forward+backward, upstream gradients on every output) and EnvLight.build_mips forward+backward
+    composed from its own renderutils plugin ops exactly like scene/light.py:72-86 + scene/renderutils/ops.py:391-458
+    (torch avg_pool2d for cubemap_mip's forward; its backward needs nvdiffrast and is left out, like the shading)."""
+    name = "reference"
+
+    def __init__(self, dev, rank, world, wl):
+        super().__init__(dev, rank, world, wl)
+        import importlib
+        ref_dir = ROOT / "oracle" / "_ref"
+        if not (ref_dir / "diff_surfel_rasterization").exists():
+            raise RuntimeError("oracle/_ref is not available")
+        sys.path.insert(0, str(ref_dir))
+        ref = importlib.import_module("diff_surfel_rasterization")
+        self.GRS, self.GR = ref.GaussianRasterizationSettings, ref.GaussianRasterizer
+        self.plugin = None
+        if wl["shade"] and (ref_dir / "renderutils_plugin" / "renderutils_plugin.so").exists():
+            sys.path.insert(0, str(ref_dir / "renderutils_plugin"))
+            self.plugin = importlib.import_module("renderutils_plugin")
+            self.base = self.base_init.to(dev).requires_grad_(True)
+            res, n = wl["cube_res"], 1
+            while res > wl["min_res"]:
+                res //= 2
+                n += 1
+            rough = [(i / (n - 2)) * (0.5 - 0.08) + 0.08 for i in range(n - 1)] + [1.0]
+            self.keys = []
+            for l, r in enumerate(rough):          # __ndfBounds, cached per key like ops.py:428-443
+                ct = self._cutoff_costheta(r, 0.99)
+                self.keys.append((r, ct, self.plugin.specular_bounds(wl["cube_res"] >> l, ct)))
+            rng = torch.Generator().manual_seed(5)
+            self.g_levels = [torch.randn(6, wl["cube_res"] >> l, wl["cube_res"] >> l, 4, generator=rng).to(dev) * 1e-6
+                             for l in range(n)]
+            self.g_diffuse = torch.randn(6, wl["min_res"], wl["min_res"], 3, generator=rng).to(dev) * 1e-6
+
+    def upstream_keys(self):
+        return ("render", "allmap", "feature")
+
+    @staticmethod
+    def _cutoff_costheta(roughness, cutoff):
+        """scene/renderutils/ops.py:428-441."""
+        def ndf(alphaSqr, costheta):
+            costheta = np.clip(costheta, 0.0, 1.0)
+            d = (costheta * alphaSqr - costheta) * costheta + 1.0
+            return alphaSqr / (d * d * np.pi)
+        costheta = np.cos(np.linspace(0, np.pi / 2.0, 1000000))
+        D = np.cumsum(ndf(roughness ** 4, costheta))
+        return float(costheta[np.argmax(D >= D[..., -1] * cutoff)])
+
+    def begin_step(self):
+        for t in (*self.leaves.values(), self.means2D):
+            t.grad = None
+        if self.plugin is not None and self.train:   # build_mips forward (scene/light.py:72-86)
+            p = self.plugin
+            raw = [self.base.detach()]
+            while raw[-1].shape[1] > self.wl["min_res"]:
+                raw.append(torch.nn.functional.avg_pool2d(raw[-1].permute(0, 3, 1, 2), (2, 2)).permute(0, 2, 3, 1).contiguous())
+            self.raw = raw
+            self.diffuse = p.diffuse_cubemap_fwd(raw[-1])
+            self.specular = []
+            for lvl, (r, ct, b) in zip(raw, self.keys):
+                o4 = p.specular_cubemap_fwd(lvl, b, r, ct)
+                self.specular.append(o4[..., 0:3] / o4[..., 3:])
+
+    def end_step(self):
+        if self.plugin is not None and self.train:   # build_mips backward, per level (ops.py:407-411, :421-426)
+            p = self.plugin
+            g = p.diffuse_cubemap_bwd(self.raw[-1], self.g_diffuse)
+            for lvl, (r, ct, b), d4 in zip(self.raw, self.keys, self.g_levels):
+                g = p.specular_cubemap_bwd(lvl, b, d4, r, ct)
+            self.base.grad = g if g.shape == self.base.shape else None
+
+    def render(self, view, cam_mats, up, last=False):
         cam = self.cams[view]
         wvt, proj, center = cam_mats
         rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, wvt, proj,
-                      WORKLOAD["sh_degree"], center, False, False)
+                      self.wl["sh_degree"], center, False, False)
         L = self.leaves
-        contrib, color, feat, radii, allmap = (self.GR(rs, grad_sink=self.sink) if self.sink is not None else self.GR(rs))(
-            means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
-            features=L["features"], scales=L["scales"], rotations=L["rotations"])
-        loss = (color * up["render"]).sum() + (allmap * up["allmap"]).sum() + (feat * self.up_feat).sum()
-        loss.backward()
+        with torch.set_grad_enabled(self.train):
+            contrib, color, feat, radii, allmap = self.GR(rs)(
+                means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
+                features=L["features"], scales=L["scales"], rotations=L["rotations"])
+            loss = None
+            if self.train:
+                loss = (color * up["render"]).sum() + (allmap * up["allmap"]).sum() + (feat * up["feature"]).sum()
+                loss.backward()
         self.last = {"radii": radii, "render": color, "loss": loss}
         return loss
 
@@ -350,44 +507,44 @@ def algorithmic_bytes(P, Pv, R, N, S=8, D=3, M=16):
     b = {
         "render_fwd": R * rec + N * 4 * (15 + S),
         "render_bwd": R * rec + N * 4 * (15 + S) + P * 4 * (18 + S),
+        "preprocess_fwd": 48 * P + (12 * (D + 1) ** 2 + 79) * Pv,
+        "preprocess_bwd": (47 + 12 * (D + 1) ** 2 + 68) * Pv + (48 + 12 * M) * P,
+        "sort": 24 * R,
     }
     b["frame_raster"] = (56 * P + 291 * Pv + 156 * R + 92 * N) + (344 * P + 307 * Pv + 112 * R + 92 * N)
-    b["frame_shade"] = 192 * N + 2 * 25_165_056 // 1  # + cubemap-chain read and gradient (25.2 MB each)
+    b["frame_shade"] = 192 * N
     return b
 
 
-def cpu_baseline(cores_hint=None):
-    """CPU oracle port (oracle/surfel_oracle.cpp, OpenMP) on a bounded sample of the SAME workload:
-    full preprocessing + binning of the 1 M surfel frame, forward+backward blending of every 8th tile."""
+def cpu_baseline(wl):
+    """CPU oracle port (oracle/surfel_oracle.cpp, OpenMP, all host cores) on ONE full frame of the SAME workload:
+    preprocess + binning + forward and backward blending of every tile (no extrapolation). Rasterizer only."""
     from materialrefgs_b200 import synthetic
     from oracle import surfel_oracle as so
-    w = WORKLOAD
-    cloud = synthetic.make_cloud(w["P"], S=w["S"], opacity=w["opacity"])
-    cam = synthetic.orbit_camera(1, 8, w["W"], w["H"])
-    gc, gf, go = synthetic.upstream_grads(w["S"], w["H"], w["W"])
+    cloud = synthetic.make_cloud(wl["P"], S=wl["S"], opacity=wl["opacity"], unbounded=wl["unbounded"])
+    cam = synthetic.orbit_camera(1, N_CAMS, wl["W"], wl["H"], radius=wl["radius"])
+    gc, gf, go = synthetic.upstream_grads(wl["S"], wl["H"], wl["W"])
     o = so.from_synthetic(cloud, cam)
-    step = 8
     t0 = time.perf_counter()
     o.preprocess(); o.bin()
     t1 = time.perf_counter()
-    o.forward(tile_step=step)
-    o.backward(gc.numpy(), gf.numpy(), go.numpy(), tile_step=step)
+    o.forward()
+    o.backward(gc.numpy(), gf.numpy(), go.numpy())
     t2 = time.perf_counter()
-    est = (t1 - t0) + (t2 - t1) * step
-    return {"value": 1.0 / est, "unit": "frames/s", "cores": so.lib().oracle_num_threads(), "kind": "port",
-            "sample": f"1M-surfel 800x800 frame: preprocess+binning in full ({t1 - t0:.1f}s), fwd+bwd blend of every "
-                      f"{step}th tile ({t2 - t1:.1f}s, scaled x{step}); rasterizer only"}
+    return {"value": 1.0 / (t2 - t0), "unit": "frames/s", "cores": so.lib().oracle_num_threads(), "kind": "port",
+            "sample": f"one full {wl['P']}-surfel {wl['W']}x{wl['H']} frame: preprocess+binning {t1 - t0:.1f}s, fwd+bwd blend of "
+                      f"all tiles {t2 - t1:.1f}s; rasterizer only (no build_mips, no shading)"}
 
 
-def cpu_shading_baseline():
+def cpu_shading_baseline(wl):
     """Config C1: torch-CPU split-sum deferred shading (the reference's own shading is torch + nvdiffrast)."""
     from materialrefgs_b200 import synthetic
     from oracle import shading_oracle as so
     torch.set_num_threads(os.cpu_count() or 1)
-    H, W = WORKLOAD["H"], WORKLOAD["W"]
-    cam = synthetic.orbit_camera(1, 8, W, H)
+    H, W = wl["H"], wl["W"]
+    cam = synthetic.orbit_camera(1, N_CAMS, W, H)
     base, feats, allmap = so.synthetic_gbuffer(H, W)
-    levels = [l.requires_grad_(True) for l in so.synthetic_chain(WORKLOAD["cube_res"], WORKLOAD["min_res"])]
+    levels = [l.requires_grad_(True) for l in so.synthetic_chain(wl["cube_res"], wl["min_res"])]
     feats.requires_grad_(True)
     env, lut, bg = so.EnvLightOracle(levels), so.load_lut(), torch.zeros(3)
     ts = []
@@ -401,20 +558,34 @@ def cpu_shading_baseline():
             "sample": "800x800 G-buffer, 6x512^2 cubemap chain, 1 warm-up + 3 timed, median"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the tracked summary that
+    tools/ncu_traffic.py writes from an `ncu --set full` capture of this workload (profiles/ncu_traffic.json)."""
+    p = ROOT / "profiles" / "ncu_traffic.json"
+    try:
+        d = json.loads(p.read_text())
+        e = d["kernels"][kernel]
+        return float(e["dram_bytes_per_launch"]), d.get("source")
+    except Exception:
+        return None, None
+
+
 def main():
-    global VIEWS_PER_RANK
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="C3", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the surfel count (debug only)")
-    ap.add_argument("--views-per-rank", type=int, default=VIEWS_PER_RANK)
+    ap.add_argument("--views-per-rank", type=int, default=None)
     a = ap.parse_args()
-    VIEWS_PER_RANK = max(1, a.views_per_rank)
+    wl = dict(WORKLOADS[a.config])
+    if a.views_per_rank:
+        wl["views_per_rank"] = max(1, a.views_per_rank)
     if a.P:
-        WORKLOAD["P"] = a.P
+        wl["P"] = a.P
     a.warmup = max(a.warmup, 3)
 
     if not torch.cuda.is_available():
@@ -428,29 +599,33 @@ def main():
         rank, local, world = 0, int(os.environ.get("LOCAL_RANK", "0")), 1
         torch.cuda.set_device(local)
     else:
-        rank, local, world = dist_setup(a.gpus)
+        rank, local, world = dist_setup()
     dev = torch.device("cuda", local)
 
     if a.impl == "reference":
-        world_eff = 1
         try:
-            stepper = ReferenceStep(dev, 0, 1)
+            stepper = ReferenceStep(dev, 0, 1, wl)
         except Exception as ex:  # oracle/_ref missing: time the CPU oracle port instead
-            cb = cpu_baseline()
-            line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "frames/s", "n_gpus": 0,
+            cb = cpu_baseline(wl)
+            line = {"impl": "reference", "metric": wl["metric"], "value": cb["value"], "unit": "frames/s", "n_gpus": 0,
                     "steps": 1, "warmup": 0, "ms_per_step": 1000.0 / cb["value"], "higher_is_better": True,
-                    "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                    "config": {"workload": "C3 rasterizer only, CPU oracle port", "note": str(ex)},
+                    "scaling": wl["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                    "config": {"workload": a.config + " rasterizer only, CPU oracle port", "note": str(ex)},
                     "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "frames/s", "h2d_bytes_per_step": 0,
                                                 "d2h_bytes_per_step": 0}}
             print(json.dumps(line))
             return 0
     else:
-        world_eff = world
-        stepper = OursStep(dev, rank, world)
+        stepper = OursStep(dev, rank, world, wl)
+    ours = a.impl == "ours"
 
-    from materialrefgs_b200 import _lib
-    lib = _lib.load()
+    # every rank learns every camera's cost once (forward only, untimed): the view schedule is then identical everywhere
+    if ours and world > 1:
+        with torch.no_grad():
+            for v in range(N_CAMS):
+                c = stepper.cam_dev[v]
+                stepper.render(v, (c.world_view_transform, c.full_proj_transform, c.camera_center), stepper.up)
+        torch.cuda.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------
     sampler = ClockSampler(local)
@@ -458,115 +633,140 @@ def main():
         sampler.start()           # started before the warm-up so its own start-up cost is not timed
     for i in range(a.warmup):
         stepper.step(i)
-    barrier(world_eff)
-    lib.mrgs_profile_enable(1)
-    lib.mrgs_profile_reset()
+    barrier(world)
+    if ours:
+        stepper.lib.mrgs_profile_enable(1)
+        stepper.lib.mrgs_profile_reset()
+        launches0 = int(stepper.lib.mrgs_launch_count())
     if rank == 0:
         sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier(world_eff)
+    barrier(world)
     e0.record()
     for i in range(a.steps):
         stepper.step(a.warmup + i)
     e1.record()
-    barrier(world_eff)
+    barrier(world)
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
-    prof = _lib.profile_read()
-    launches = int(lib.mrgs_launch_count())
-    lib.mrgs_profile_enable(0)
-    if world_eff > 1:
+    if ours:
+        prof = stepper._lib.profile_read()
+        launches = int(stepper.lib.mrgs_launch_count()) - launches0
+        stepper.lib.mrgs_profile_enable(0)
+    if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / a.steps
-    value = world_eff * VIEWS_PER_RANK * 1000.0 / ms_per_step
+    views_per_step = stepper.total_views
+    value = views_per_step * 1000.0 / ms_per_step
 
     # ---- end-to-end timing: pinned host inputs -> device, result -> host, every step ----------
     for i in range(2):
         stepper.step(i, e2e=True)
     stepper.e2e_finish()
-    barrier(world_eff)
+    barrier(world)
     t0 = time.perf_counter()
     for i in range(a.steps):
         stepper.step(a.warmup + i, e2e=True)
     stepper.e2e_finish()          # the last step's results are read inside the timed region too
-    barrier(world_eff)
+    barrier(world)
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / a.steps
-    if world_eff > 1:
+    if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
+        h2d = torch.tensor([float(stepper.h2d_bytes()), float(stepper.d2h_bytes())], device=dev)
+        dist.all_reduce(h2d)
+        h2d_bytes, d2h_bytes = int(h2d[0].item()), int(h2d[1].item())
+    else:
+        h2d_bytes, d2h_bytes = stepper.h2d_bytes(), stepper.d2h_bytes()
 
     if rank != 0:
         return 0
 
     radii = stepper.last["radii"]
-    P, N = WORKLOAD["P"], WORKLOAD["H"] * WORKLOAD["W"]
+    P, N = wl["P"], wl["H"] * wl["W"]
     Pv = int((radii > 0).sum())
+    par = f"view-sharded x{world}"
+    if world > 1 and stepper.train:
+        par += (" + ONE NCCL sum-allreduce of the flat [P*68-float gradient+statistics arena | cubemap texel-gradient sink] buffer "
+                "(sink part issued under the last view's rasterizer backward, arena part overlapped with the build_mips backward) "
+                "+ one int32 max-allreduce of max_radii2D; views dealt to ranks by cost (LPT on last-seen instance counts)")
     line = {
-        "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world_eff, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "metric": wl["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": wl["scaling"],
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "C3: 1M random-init surfels (trained-like opacity), 800x800, S=8 material channels, "
-                               "SH degree 3, rasterize + fused deferred PBR shading (6x512^2 cubemap, 6 mips), fwd+bwd",
-                   "P": P, "Pv": Pv, "N": N, "S": WORKLOAD["S"], "views_per_step": world_eff * VIEWS_PER_RANK, "views_per_rank": VIEWS_PER_RANK,
-                   "parallelism": f"view-sharded x{world_eff}" + (" + 1 NCCL allreduce of the P*68-float gradient+statistics arena + 1 of the 33 MB environment-map gradient sink" if world_eff > 1 else ""),
-                   "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient arenas) exceeds the 126 MB L2"},
-        "e2e": {"value": world_eff * VIEWS_PER_RANK * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": stepper.h2d_bytes(),
-                "d2h_bytes_per_step": stepper.d2h_bytes(),
-                "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss of every view read back to pinned host memory and consumed by the host one step later (double-buffered, like asynchronous logging), the last step's before the clock stops; surfel parameters are model state resident in HBM"},
+        "config": {"workload": wl["text"], "name": a.config,
+                   "P": P, "Pv": Pv, "N": N, "S": wl["S"], "views_per_step": views_per_step,
+                   "views_per_rank": stepper.V, "parallelism": par,
+                   "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient "
+                         "arenas + 2 x 5 GB of prefilter weights streamed once per step) exceeds the 126 MB L2"},
+        "e2e": {"value": views_per_step * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                "d2h_bytes_per_step": d2h_bytes,
+                "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss of every "
+                        "view read back to pinned host memory and consumed by the host one step later (double-buffered, like "
+                        "asynchronous logging), the last step's before the clock stops; surfel parameters and the cubemap are "
+                        "model state resident in HBM"},
         "clocks": clocks,
     }
-    if a.impl == "reference":
+    if not ours:
         line["impl"] = "reference"
         line["gpu_launches"] = 0
-        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference",
-                                "sample": "unmodified reference CUDA rasterizer (oracle/_ref rebuilt for sm_100a) through its own "
-                                          "Python API on this B200, rasterize fwd+bwd ONLY (its nvdiffrast shading cannot run here, so this "
-                                          "arm does less work than ours); the reference has no CPU rasterizer"}
-        line["config"]["workload"] += " [reference arm: rasterizer fwd+bwd only, no shading]"
+        what = ("unmodified reference CUDA rasterizer (oracle/_ref rebuilt for sm_100a) through its own Python API on this B200, "
+                "rasterize fwd+bwd per view")
+        what += (" + EnvLight.build_mips fwd+bwd per step through the reference's own renderutils plugin ops (cubemap_mip backward "
+                 "left out: needs nvdiffrast)" if stepper.plugin is not None else "")
+        what += "; its nvdiffrast shading cannot run here, so this arm does less work than ours; the reference has no CPU rasterizer"
+        line["cpu_baseline"] = {"value": value, "unit": "frames/s", "cores": os.cpu_count(), "kind": "reference", "sample": what}
+        line["config"]["workload"] += " [reference arm: build_mips via its plugin + rasterizer fwd+bwd, no shading]"
         print(json.dumps(line))
         return 0
 
     stage_ms = {k: (v[0] / v[1] if v[1] else 0.0) for k, v in prof.items()}
-    # instance count R: read it back from the scan output of the last frame (not timed)
-    from materialrefgs_b200 import rasterizer as rz
-    c = stepper.cam_dev[0]
-    e = torch.empty(0, device=dev)
-    with torch.no_grad():
-        R = rz.rasterize_forward_raw(stepper.bg, stepper.cloud.means3D, e, stepper.cloud.features, stepper.cloud.opacities,
-                                     stepper.cloud.scales, stepper.cloud.rotations, 1.0, e, c.world_view_transform,
-                                     c.full_proj_transform, c.tanfovx, c.tanfovy, WORKLOAD["H"], WORKLOAD["W"],
-                                     stepper.cloud.shs, 3, c.camera_center, False, False)[0]
-    ab = algorithmic_bytes(P, Pv, R, N, WORKLOAD["S"])
-    peak, peak_kind = measured_peak_hbm()
-    dom = max(("render_fwd", "render_bwd"), key=lambda k: stage_ms[k])
-    achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
-    line["config"]["R"] = int(R)
-    tiles = ((WORKLOAD["W"] + 15) // 16) * ((WORKLOAD["H"] + 15) // 16)
-    line["config"]["tiles"] = tiles
-    line["config"]["mean_tile_list_length"] = round(int(R) / tiles, 1)
+    stage_calls = {k: v[1] for k, v in prof.items()}
     line["gpu_launches"] = launches
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of this workload
-    # (profiles/r01_v7_summary.md); only valid for the default C3 workload
-    traffic = {"render_bwd": 103.9e6 + 6.0e6, "render_fwd": 32.2e6 + 13.6e6}.get(dom) if WORKLOAD["P"] == 1_000_000 else None
-    line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": traffic, "peak_kind": peak_kind,
-                        "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": stage_ms[dom],
-                        "note": "tile-blend kernels are instruction-issue bound (ncu: issue slots 72-78 % busy, DRAM ~1.5 % of peak), "
-                                "not HBM bound; DRAM traffic is ~10x below the algorithmic bytes because neighbouring tiles share "
-                                "list entries in L2; see profiles/r01_v7_summary.md"}
-    frame_bytes = ab["frame_raster"] + ab["frame_shade"]
-    ms_per_frame = ms_per_step / VIEWS_PER_RANK
-    line["frame_roofline"] = {"algorithmic_bytes_per_frame": frame_bytes,
-                              "achieved_gbs": frame_bytes / (ms_per_frame * 1e-3) / 1e9,
-                              "frac": frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak}
+    if stepper.train:
+        R = int(stepper.cost[stepper.views_for_step(a.warmup + a.steps - 1)[-1]]) if stepper.V else 0
+        ab = algorithmic_bytes(P, Pv, R, N, wl["S"])
+        peak, peak_kind = measured_peak_hbm()
+        tiles = ((wl["W"] + 15) // 16) * ((wl["H"] + 15) // 16)
+        line["config"].update({"R": R, "tiles": tiles, "mean_tile_list_length": round(R / tiles, 1)})
+        dom = max(("render_fwd", "render_bwd"), key=lambda k: stage_ms[k])
+        achieved = ab[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms[dom] > 0 else 0.0
+        traffic, src = ncu_traffic(dom) if a.config == "C3" else (None, None)
+        line["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                            "frac": achieved / peak, "traffic": traffic, "traffic_source": src, "peak_kind": peak_kind,
+                            "algorithmic_bytes_per_launch": ab[dom], "avg_launch_ms": stage_ms[dom],
+                            "note": "dominant kernel by share of the step; the tile-blend kernels are instruction-issue bound "
+                                    "(ncu: issue slots 72-78 % busy), DRAM traffic is ~10x below the algorithmic bytes because "
+                                    "neighbouring tiles share list entries in L2; see profiles/"}
+        others = {}
+        for k in ("preprocess_fwd", "preprocess_bwd", "sort"):
+            if stage_ms.get(k, 0) > 0:
+                others[k] = {"algorithmic_bytes": ab[k], "ms": stage_ms[k], "frac": ab[k] / (stage_ms[k] * 1e-3) / 1e9 / peak}
+        if stepper.env is not None and stepper.env._chain is not None:
+            ch = stepper.env._chain
+            taps = sum(p[0].taps for p in ch.spec) + ch.diff[0].taps
+            plan_f = sum(p[0].nbytes for p in ch.spec) + ch.diff[0].nbytes
+            alg = 4 * taps + 28 * ch.texels     # every tap's weight once + source (16 B) and destination (12 B) texels once
+            for k in ("prefilter_fwd", "prefilter_bwd"):
+                # a stage sample = mean over its scopes (gather + pyramid / mip-backward chain); the step total is what counts
+                tot = stage_ms[k] * stage_calls[k] / max(a.steps, 1)
+                others[k] = {"algorithmic_bytes": alg, "plan_bytes": plan_f, "ms_per_step": tot,
+                             "frac": alg / (tot * 1e-3) / 1e9 / peak if tot > 0 else None, "taps": taps}
+        line["stage_rooflines"] = others
+        frame_bytes = ab["frame_raster"] + (ab["frame_shade"] if wl["shade"] else 0)
+        ms_per_frame = ms_per_step / max(stepper.V, 1)
+        line["frame_roofline"] = {"algorithmic_bytes_per_frame": frame_bytes,
+                                  "achieved_gbs": frame_bytes / (ms_per_frame * 1e-3) / 1e9,
+                                  "frac": frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak}
     line["stage_ms"] = stage_ms
-    if not a.no_cpu_baseline and world_eff == 1:
-        line["cpu_baseline"] = cpu_baseline()
-        line["cpu_shading_baseline"] = cpu_shading_baseline()
+    line["stage_calls_per_step"] = {k: v / max(a.steps, 1) for k, v in stage_calls.items()}
+    if not a.no_cpu_baseline and world == 1 and a.config == "C3":
+        line["cpu_baseline"] = cpu_baseline(wl)
+        line["cpu_shading_baseline"] = cpu_shading_baseline(wl)
     print(json.dumps(line))
     return 0
 

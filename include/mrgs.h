@@ -38,7 +38,8 @@
  *   mrgs_densify_stats  <- GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061
  *
  * ABI history: 5 = gradient sink (accumulate) in mrgs_backward; 6 = mrgs_geometry_loss_*, mrgs_img_grad_weight,
- * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query.
+ * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query;
+ * 7 = prefilter plans (mrgs_prefilter_*), mrgs_mip_pyramid_forward, mrgs_mip_chain_backward.
  */
 #ifndef MRGS_H_INCLUDED
 #define MRGS_H_INCLUDED
@@ -50,7 +51,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 6
+#define MRGS_ABI_VERSION 7
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -239,7 +240,9 @@ MRGS_API int32_t mrgs_grad_arena_stride(int32_t S);
 #define MRGS_STAGE_SHADE_BWD 9
 #define MRGS_STAGE_CUBEMAP 10
 #define MRGS_STAGE_DEPTH_SORT 11
-#define MRGS_STAGE_COUNT 12
+#define MRGS_STAGE_PREFILTER_FWD 12
+#define MRGS_STAGE_PREFILTER_BWD 13
+#define MRGS_STAGE_COUNT 14
 MRGS_API void mrgs_profile_enable(int32_t on);
 MRGS_API void mrgs_profile_reset(void);
 MRGS_API int mrgs_profile_read(double* ms, int64_t* calls, int32_t n);
@@ -375,6 +378,100 @@ MRGS_API int mrgs_specular_cubemap_backward(const float* cubemap, const int32_t*
 MRGS_API int mrgs_diffuse_cubemap_forward(const float* cubemap, int32_t res, float* out, void* stream);
 MRGS_API int mrgs_diffuse_cubemap_backward(const float* cubemap, int32_t res, const float* dout, float* dcubemap,
                                            void* stream);
+
+/* ---- EnvLight.build_mips as a precomputed sparse operator ("prefilter plan") --------------------------
+ * The reference runs build_mips() every training iteration (train_refnerf.py:1155-1163, scene/light.py:72-86):
+ * cubemap_mip down to min_res, ru.diffuse_cubemap on the smallest level and ru.specular_cubemap(level, roughness,
+ * cutoff) on every level (scene/renderutils/ops.py:391-458, kernels c_src/cubemap.cu:110-354). For a fixed
+ * (res, roughness, cutoff) those two ops are fixed linear maps of the cubemap; a plan stores one of them (or its
+ * transpose, for the backward) as per-destination-texel tap lists with the tap weights the reference would compute
+ * (same expression order, same loop domain = its cached bounds incl. the 16x16 tile culling), already divided by
+ * the reference-order weight sum. Applying a plan is a gather: no atomics, no zero fill, every weight read once.
+ *
+ * A plan is built in two passes over caller-owned memory:
+ *   1. mrgs_prefilter_plan_count: per patch (one warp's destination texels, see below) the number of source-row
+ *      segments, weight rows and taps; for MRGS_PREFILTER_SPECULAR also wsum[texel] (the un-normalised weight sum
+ *      = channel 3 of specular_cubemap_fwd's output) unless wsum is NULL (counts only: used to pick the patch shape).
+ *   2. the caller turns the counts into exclusive prefix sums (patch_seg_begin / patch_slot_begin, patches+1
+ *      entries), allocates seg_desc [segments][2] int32, spans [segments][32] uint16, weights
+ *      [rows][rows_per_lane][32] float and calls mrgs_prefilter_plan_fill.
+ * kinds: _SPECULAR   dst = GGX-prefiltered level, src = raw level            (specular_cubemap fwd, normalised)
+ *        _SPECULAR_T dst = d(raw level),          src = d(prefiltered level) (specular_cubemap bwd incl. the
+ *                    division by wsum); needs wsum and bounds of every texel; full_search = 1 searches the whole
+ *                    cube for every texel (needed when the reference's tile culling is not conservative: the caller
+ *                    compares the tap totals of both orientations)
+ *        _DIFFUSE / _DIFFUSE_T  the cosine convolution and its transpose (no bounds, no normalisation)
+ * Patch shape: patch_width (32, 16 or 8 lanes) x (32 / patch_width * rows_per_lane) texels of one face, a lane
+ * owning rows_per_lane (1 or 2) vertically adjacent texels; (32, 1) is the linear layout (32 consecutive texels in
+ * memory order) and works for any res, the others need res divisible by the block's width and height. Padded
+ * weight slots (a segment is as long as its longest lane) depend on the shape: callers run the count pass per shape
+ * and keep the smallest. */
+#define MRGS_PREFILTER_SPECULAR 0
+#define MRGS_PREFILTER_SPECULAR_T 1
+#define MRGS_PREFILTER_DIFFUSE 2
+#define MRGS_PREFILTER_DIFFUSE_T 3
+#define MRGS_PREFILTER_MAX_JOBS 8
+
+typedef struct MrgsPrefilterPlan {
+    int32_t res;
+    int32_t rows_per_lane;
+    int32_t patch_width;
+    int32_t* patch_seg_begin;
+    int32_t* patch_slot_begin;
+    int32_t* seg_desc;
+    uint16_t* spans;
+    float* weights;
+} MrgsPrefilterPlan;
+
+typedef struct MrgsPrefilterBuildArgs {
+    int32_t kind;
+    int32_t res;
+    int32_t rows_per_lane;
+    int32_t patch_width;
+    int32_t full_search;
+    float roughness;
+    float costheta_cutoff;
+    const float* texel_table;   /* [6][res][res][4] from mrgs_prefilter_texel_table */
+    const int32_t* bounds;      /* [6][res][res][6][4] from mrgs_specular_bounds (specular kinds) */
+    float* wsum;                /* [6][res][res]: written by the count pass of _SPECULAR, read otherwise */
+    int32_t* seg_count;         /* count pass outputs, one entry per patch */
+    int32_t* slot_count;
+    int32_t* tap_count;
+    MrgsPrefilterPlan plan;     /* fill pass: prefix sums in, seg_desc / spans / weights out */
+} MrgsPrefilterBuildArgs;
+
+/* one gather: dst[texel] = sum over the texel's taps of weight * src[tap]; rgb at src/dst_stride floats per texel
+ * (3 or 4). nan_where_zero (optional, [texels]): destination texels whose entry is 0 receive NaN, which is what
+ * the reference's rgb / wsum yields for an empty cone. */
+typedef struct MrgsPrefilterJob {
+    MrgsPrefilterPlan plan;
+    const float* src;
+    float* dst;
+    const float* nan_where_zero;
+    int32_t src_stride;
+    int32_t dst_stride;
+} MrgsPrefilterJob;
+
+/* number of patches (= warps of the gather), or -1 when the shape does not tile a res x res face */
+MRGS_API int32_t mrgs_prefilter_patch_count(int32_t res, int32_t rows_per_lane, int32_t patch_width);
+MRGS_API int mrgs_prefilter_texel_table(int32_t res, float* table, void* stream);
+MRGS_API int mrgs_prefilter_plan_count(const MrgsPrefilterBuildArgs* args, void* stream);
+MRGS_API int mrgs_prefilter_plan_fill(const MrgsPrefilterBuildArgs* args, void* stream);
+/* All jobs (at most MRGS_PREFILTER_MAX_JOBS: the levels of a chain + its diffuse map) in ONE launch, in the order
+ * given (put the jobs with the longest tap lists first). backward != 0 only selects the profiling stage. */
+MRGS_API int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, void* stream);
+/* base [6][res][res][3] -> levels4[0] = float4-padded copy of it, levels4[l] = [6][res>>l][res>>l][4] 2x2 averages
+ * (cubemap_mip forward, scene/light_utils.py:69-71, for the whole chain in one launch per 5 levels).
+ * levels4 is a HOST array of num_levels device pointers; res must be divisible by 2^(num_levels-1). */
+MRGS_API int mrgs_mip_pyramid_forward(const float* base, int32_t res, int32_t num_levels, float* const* levels4,
+                                      void* stream);
+/* grads3[l] ([6][res>>l][res>>l][3], HOST array of device pointers) holds d(raw level l) from the level's own
+ * prefilter; on return grads3[l] += cubemap_mip backward (the reference's non-adjoint bilinear fetch,
+ * scene/light_utils.py:72-80) of the completed grads3[l+1], from the coarsest level down, so grads3[0] is the
+ * gradient of the base cubemap. extra_last3 (optional) is added to the coarsest level first (the diffuse map's
+ * gradient, which the reference's autograd sums into the same tensor). */
+MRGS_API int mrgs_mip_chain_backward(int32_t res, int32_t num_levels, float* const* grads3, const float* extra_last3,
+                                     void* stream);
 
 MRGS_API int mrgs_forward(MrgsForwardArgs* args, void* stream);
 MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);

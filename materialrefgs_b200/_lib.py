@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 6
+MRGS_ABI_VERSION = 7
 MAX_FEATURES = 24
 TILE = 16
 
@@ -121,6 +121,28 @@ class GeometryLossArgs(C.Structure):
         "upstream", "dL_drend_normal", "dL_dsurf_normal", "dL_drend_dist", "dL_dsurf_depth")]
 
 
+PREFILTER_SPECULAR, PREFILTER_SPECULAR_T, PREFILTER_DIFFUSE, PREFILTER_DIFFUSE_T = 0, 1, 2, 3
+PREFILTER_MAX_JOBS = 8
+
+
+class PrefilterPlan(C.Structure):
+    """MrgsPrefilterPlan (include/mrgs.h)."""
+    _fields_ = [("res", C.c_int32), ("rows_per_lane", C.c_int32), ("patch_width", C.c_int32)] + [(n, _fp) for n in (
+        "patch_seg_begin", "patch_slot_begin", "seg_desc", "spans", "weights")]
+
+
+class PrefilterBuildArgs(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("res", C.c_int32), ("rows_per_lane", C.c_int32), ("patch_width", C.c_int32),
+                ("full_search", C.c_int32),
+                ("roughness", C.c_float), ("costheta_cutoff", C.c_float)] + [(n, _fp) for n in (
+        "texel_table", "bounds", "wsum", "seg_count", "slot_count", "tap_count")] + [("plan", PrefilterPlan)]
+
+
+class PrefilterJob(C.Structure):
+    _fields_ = [("plan", PrefilterPlan), ("src", _fp), ("dst", _fp), ("nan_where_zero", _fp),
+                ("src_stride", C.c_int32), ("dst_stride", C.c_int32)]
+
+
 SYMBOLS = {
     "mrgs_abi_version": (C.c_int, []),
     "mrgs_last_error": (C.c_char_p, []),
@@ -154,6 +176,13 @@ SYMBOLS = {
     "mrgs_specular_cubemap_backward": (C.c_int, [_fp, _fp, C.c_int32, C.c_float, C.c_float, _fp, _fp, C.c_void_p]),
     "mrgs_diffuse_cubemap_forward": (C.c_int, [_fp, C.c_int32, _fp, C.c_void_p]),
     "mrgs_diffuse_cubemap_backward": (C.c_int, [_fp, C.c_int32, _fp, _fp, C.c_void_p]),
+    "mrgs_prefilter_patch_count": (C.c_int32, [C.c_int32, C.c_int32, C.c_int32]),
+    "mrgs_prefilter_texel_table": (C.c_int, [C.c_int32, _fp, C.c_void_p]),
+    "mrgs_prefilter_plan_count": (C.c_int, [C.POINTER(PrefilterBuildArgs), C.c_void_p]),
+    "mrgs_prefilter_plan_fill": (C.c_int, [C.POINTER(PrefilterBuildArgs), C.c_void_p]),
+    "mrgs_prefilter_apply": (C.c_int, [C.POINTER(PrefilterJob), C.c_int32, C.c_int32, C.c_void_p]),
+    "mrgs_mip_pyramid_forward": (C.c_int, [_fp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
+    "mrgs_mip_chain_backward": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _fp, C.c_void_p]),
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),
     "mrgs_backward": (C.c_int, [C.POINTER(BackwardArgs), C.c_void_p]),
     "mrgs_mark_visible": (C.c_int, [C.c_int32, _fp, _fp, _fp, _fp, C.c_void_p]),
@@ -206,7 +235,7 @@ def load() -> C.CDLL:
 
 
 STAGES = ("preprocess_fwd", "scan", "duplicate", "sort", "ranges", "render_fwd", "render_bwd",
-          "preprocess_bwd", "shade_fwd", "shade_bwd", "cubemap", "depth_sort")
+          "preprocess_bwd", "shade_fwd", "shade_bwd", "cubemap", "depth_sort", "prefilter_fwd", "prefilter_bwd")
 
 
 def profile_read() -> dict:

@@ -31,6 +31,7 @@ SOURCES = [
     "preprocess_bwd.cu",
     "shade.cu",
     "cubemap.cu",
+    "prefilter.cu",
     "features.cu",
     "losses.cu",
     "geomloss.cu",

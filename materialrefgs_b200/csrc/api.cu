@@ -453,10 +453,13 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         // depth order of the surfels, then instance offsets in that order
         uint32_t* order = nullptr;
         {
-            int launches = 0;
-            StageScope sc(MRGS_STAGE_DEPTH_SORT, stream, 0);
-            depth_sort(sort_keys_a, sort_keys_b, sort_vals_a, sort_vals_b, a->P, hist, stream, &order, &launches);
-            g_prof.launches += launches;
+            int launches = 0, sort_status;
+            {
+                StageScope sc(MRGS_STAGE_DEPTH_SORT, stream, 0);
+                sort_status = depth_sort(sort_keys_a, sort_keys_b, sort_vals_a, sort_vals_b, a->P, hist, stream, &order, &launches);
+                g_prof.launches += launches;
+            }
+            if (sort_status != MRGS_OK) return sort_status;
         }
         MRGS_LAUNCH_OK("depth_sort", stream, debug);
         {
@@ -501,11 +504,15 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
             uint16_t* keys_sorted = nullptr;
             uint32_t* vals_sorted = nullptr;
             {
-                int launches = 0;
-                StageScope sc(MRGS_STAGE_SORT, stream, 0);
-                tile_sort(keys_a, keys_b, vals_a, vals_b, (int)cap, tile_bits < 9 ? 9 : tile_bits,
-                          (uint32_t*)(bin + bl.sort_temp), stream, &keys_sorted, &vals_sorted, &launches, dev_count);
-                g_prof.launches += launches;
+                int launches = 0, sort_status;
+                {
+                    StageScope sc(MRGS_STAGE_SORT, stream, 0);
+                    sort_status = tile_sort(keys_a, keys_b, vals_a, vals_b, (int)cap, tile_bits < 9 ? 9 : tile_bits,
+                                            (uint32_t*)(bin + bl.sort_temp), stream, &keys_sorted, &vals_sorted, &launches,
+                                            dev_count);
+                    g_prof.launches += launches;
+                }
+                if (sort_status != MRGS_OK) return sort_status;
             }
             MRGS_LAUNCH_OK("tile_sort", stream, debug);
             if (vals_sorted != vals_a) {
@@ -533,7 +540,7 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
         // instead of draining the stream. If R turns out larger, the exact path below redoes the binning.
         bool rendered = false;
         const int64_t cap = a->binning_capacity;
-        if (cap > 0 && cap <= 0x7fffffff && a->binning_scratch != nullptr && radix_lookback_enabled() &&
+        if (cap > 0 && cap < (1ll << 30) && a->binning_scratch != nullptr && radix_lookback_enabled() &&
             a->binning_scratch_bytes >= mrgs_binning_bytes(cap)) {
             const int st = bin_and_render((char*)a->binning_scratch, cap, R_dev);
             if (st != MRGS_OK) return st;
@@ -781,6 +788,121 @@ int mrgs_diffuse_cubemap_backward(const float* cubemap, int32_t res, const float
         launch_diffuse_cubemap(true, res, cubemap, nullptr, dout, dcubemap, stream);
     }
     MRGS_LAUNCH_OK("diffuse_cubemap_bwd", stream, false);
+    return MRGS_OK;
+}
+
+int32_t mrgs_prefilter_patch_count(int32_t res, int32_t rows_per_lane, int32_t patch_width) {
+    return prefilter_patch_count(res, rows_per_lane, patch_width);
+}
+int mrgs_prefilter_texel_table(int32_t res, float* table, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(table && res >= 1 && res <= 32768, "mrgs_prefilter_texel_table");
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        launch_texel_table(res, table, stream);
+    }
+    MRGS_LAUNCH_OK("prefilter_texel_table", stream, false);
+    return MRGS_OK;
+}
+static int prefilter_build_check(const MrgsPrefilterBuildArgs* a, bool fill, const char* who) {
+    if (a == nullptr || a->res < 1 || a->res > 32768 || a->texel_table == nullptr || a->kind < 0 || a->kind > 3 ||
+        mrgs_prefilter_patch_count(a->res, a->rows_per_lane, a->patch_width) < 0) {
+        set_error("%s: bad arguments", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    const bool spec = a->kind == MRGS_PREFILTER_SPECULAR || a->kind == MRGS_PREFILTER_SPECULAR_T;
+    // (the count pass of _SPECULAR may run without wsum: shape selection only needs the counts)
+    if (spec && (a->bounds == nullptr || (a->wsum == nullptr && (fill || a->kind == MRGS_PREFILTER_SPECULAR_T)))) {
+        set_error("%s: the specular kinds need bounds and wsum", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (!fill && (!a->seg_count || !a->slot_count || !a->tap_count)) {
+        set_error("%s: null count outputs", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    if (fill && (!a->plan.patch_seg_begin || !a->plan.patch_slot_begin || !a->plan.seg_desc || !a->plan.spans ||
+                 !a->plan.weights)) {
+        set_error("%s: incomplete plan storage", who);
+        return MRGS_ERR_INVALID_ARGUMENT;
+    }
+    return MRGS_OK;
+}
+int mrgs_prefilter_plan_count(const MrgsPrefilterBuildArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = prefilter_build_check(a, false, "mrgs_prefilter_plan_count");
+    if (st != MRGS_OK) return st;
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        st = launch_prefilter_build(a, false, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("prefilter_plan_count", stream, false);
+    return MRGS_OK;
+}
+int mrgs_prefilter_plan_fill(const MrgsPrefilterBuildArgs* a, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int st = prefilter_build_check(a, true, "mrgs_prefilter_plan_fill");
+    if (st != MRGS_OK) return st;
+    {
+        StageScope sc(MRGS_STAGE_CUBEMAP, stream, 1);
+        st = launch_prefilter_build(a, true, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("prefilter_plan_fill", stream, false);
+    return MRGS_OK;
+}
+int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(jobs && num_jobs >= 1 && num_jobs <= MRGS_PREFILTER_MAX_JOBS, "mrgs_prefilter_apply");
+    for (int k = 0; k < num_jobs; ++k) {
+        const MrgsPrefilterJob& j = jobs[k];
+        const bool ok = j.src && j.dst && (j.src_stride == 3 || j.src_stride == 4) &&
+                        (j.dst_stride == 3 || j.dst_stride == 4) && j.plan.patch_seg_begin && j.plan.patch_slot_begin &&
+                        j.plan.seg_desc && j.plan.spans && j.plan.weights &&
+                        mrgs_prefilter_patch_count(j.plan.res, j.plan.rows_per_lane, j.plan.patch_width) >= 0 &&
+                        (j.src_stride != 4 || ((uintptr_t)j.src & 15) == 0);
+        if (!ok) {
+            set_error("mrgs_prefilter_apply: job %d is malformed", k);
+            return MRGS_ERR_INVALID_ARGUMENT;
+        }
+    }
+    int st;
+    {
+        StageScope sc(backward ? MRGS_STAGE_PREFILTER_BWD : MRGS_STAGE_PREFILTER_FWD, stream, 1);
+        st = launch_prefilter_apply(jobs, num_jobs, stream);
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("prefilter_apply", stream, false);
+    return MRGS_OK;
+}
+int mrgs_mip_pyramid_forward(const float* base, int32_t res, int32_t num_levels, float* const* levels4, void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(base && levels4 && res >= 1 && num_levels >= 1 && num_levels <= MRGS_MAX_MIP_LEVELS &&
+                        (res % (1 << (num_levels - 1))) == 0, "mrgs_mip_pyramid_forward");
+    for (int l = 0; l < num_levels; ++l) MRGS_CUBE_CHECK(levels4[l] != nullptr, "mrgs_mip_pyramid_forward");
+    int st, launches = 0;
+    {
+        StageScope sc(MRGS_STAGE_PREFILTER_FWD, stream, 0);
+        st = launch_mip_pyramid(base, res, num_levels, levels4, stream, &launches);
+        g_prof.launches += launches;
+    }
+    if (st != MRGS_OK) return st;
+    MRGS_LAUNCH_OK("mip_pyramid", stream, false);
+    return MRGS_OK;
+}
+int mrgs_mip_chain_backward(int32_t res, int32_t num_levels, float* const* grads3, const float* extra_last3,
+                            void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    MRGS_CUBE_CHECK(grads3 && res >= 1 && num_levels >= 1 && num_levels <= MRGS_MAX_MIP_LEVELS &&
+                        (res % (1 << (num_levels - 1))) == 0, "mrgs_mip_chain_backward");
+    for (int l = 0; l < num_levels; ++l) MRGS_CUBE_CHECK(grads3[l] != nullptr, "mrgs_mip_chain_backward");
+    {
+        StageScope sc(MRGS_STAGE_PREFILTER_BWD, stream, num_levels - 1);
+        for (int l = num_levels - 2; l >= 0; --l)
+            launch_mip_bwd_acc(grads3[l + 1], l == num_levels - 2 ? extra_last3 : nullptr, grads3[l], res >> (l + 1), 1,
+                               stream);
+    }
+    MRGS_LAUNCH_OK("mip_chain_backward", stream, false);
     return MRGS_OK;
 }
 

@@ -329,7 +329,7 @@ radix_scatter_kernel(const KeyT* __restrict__ keys_in, const uint32_t* __restric
                     const uint32_t sv = st[(size_t)b * kMaxBins + d];
                     const uint32_t flag = sv & ~kValueMask;
                     if (flag == 0) {
-                        if (++guard > (1 << 24)) break;  // never expected; avoids hanging the GPU on a logic error
+                        if (++guard > (1 << 24)) __trap();  // never expected: fail the launch loudly instead of hanging or sorting wrongly
                         continue;
                     }
                     excl += sv & kValueMask;
@@ -409,8 +409,12 @@ int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* val
     uint32_t* vin = vals_a;
     uint32_t* vout = vals_b;
     int launches = 0;
-    if (use_lookback()) {
-        cudaMemsetAsync(scratch, 0, (kScratchHeader + (size_t)passes * table) * sizeof(uint32_t), stream);
+    // the look-back status word keeps 30 value bits: larger inputs take the three-kernel passes (callers that need the
+    // device-side count, i.e. the optimistic path, cap their capacity below 2^30: api.cu)
+    const bool lookback = use_lookback() && (n < (1 << 30) || n_dev != nullptr);
+    if (lookback) {
+        if (cudaMemsetAsync(scratch, 0, (kScratchHeader + (size_t)passes * table) * sizeof(uint32_t), stream) != cudaSuccess)
+            return -1;
         radix_multi_hist_kernel<KeyT><<<num_blocks, kSortThreads, 0, stream>>>(kin, n, n_dev, plan, totals);
         radix_digit_scan_kernel<<<passes, 256, 0, stream>>>(totals, starts);
         launches += 2;
@@ -429,7 +433,7 @@ int radix_sort_pairs(KeyT* keys_a, KeyT* keys_b, uint32_t* vals_a, uint32_t* val
             uint32_t* tv = vin; vin = vout; vout = tv;
         }
     } else {
-        cudaMemsetAsync(totals, 0, 4 * kMaxBins * sizeof(uint32_t), stream);
+        if (cudaMemsetAsync(totals, 0, 4 * kMaxBins * sizeof(uint32_t), stream) != cudaSuccess) return -1;
         for (int pass = 0; pass < passes; ++pass) {
             const int bits = plan.bits[pass], shift = plan.shift[pass];
             uint32_t* tot = totals + (size_t)pass * kMaxBins;
@@ -621,6 +625,11 @@ int depth_sort(uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a, uint32_t* v
                cudaStream_t stream, uint32_t** order, int* launches) {
     uint32_t* kf;
     *launches = radix_sort_pairs<uint32_t>(keys_a, keys_b, vals_a, vals_b, P, 32, true, block_hist, stream, &kf, order);
+    if (*launches < 0) {
+        *launches = 0;
+        set_error("depth_sort: cudaMemsetAsync of the sort scratch failed");
+        return MRGS_ERR_CUDA;
+    }
     return MRGS_OK;
 }
 
@@ -644,6 +653,11 @@ int tile_sort(uint16_t* keys_a, uint16_t* keys_b, uint32_t* vals_a, uint32_t* va
               const uint32_t* R_dev) {
     *launches = radix_sort_pairs<uint16_t>(keys_a, keys_b, vals_a, vals_b, R, tile_bits, false, block_hist, stream,
                                            keys_sorted, vals_sorted, R_dev);
+    if (*launches < 0) {
+        *launches = 0;
+        set_error("tile_sort: cudaMemsetAsync of the sort scratch failed");
+        return MRGS_ERR_CUDA;
+    }
     return MRGS_OK;
 }
 

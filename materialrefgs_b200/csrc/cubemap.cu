@@ -10,43 +10,12 @@
 //   DiffuseCubemapFwd/BwdKernel    c_src/cubemap.cu:110-171
 // Layout: cubemaps are float [6][res][res][C] (NHWC as in the reference); bounds are int32
 // [6][res][res][6][4] = (xmin,xmax,ymin,ymax) per source face (the reference stores them as floats).
-#include "cube_sample.cuh"
 #include "kernels.cuh"
+#include "prefilter_math.cuh"
 
 namespace mrgs {
 
 namespace {
-
-__device__ __forceinline__ float pixel_area(int x, int y, int N) {
-    if (N > 1) {
-        const int H = N / 2;
-        x = abs(x - H);
-        y = abs(y - H);
-        const float dx = atanf((float)(x + 1) / (float)H) - atanf((float)x / (float)H);
-        const float dy = atanf((float)(y + 1) / (float)H) - atanf((float)y / (float)H);
-        return dx * dy;
-    }
-    return 1.0f;
-}
-
-__device__ __forceinline__ F3 normalize_safe(F3 v) {
-    const float l = sqrtf(v.x * v.x + v.y * v.y + v.z * v.z);
-    if (l > 0.0f) return {v.x / l, v.y / l, v.z / l};
-    return {0.f, 0.f, 0.f};
-}
-
-__device__ __forceinline__ F3 texel_dir(int x, int y, int side, int N) {
-    const float fx = 2.0f * (((float)x + 0.5f) / (float)N) - 1.0f;
-    const float fy = 2.0f * (((float)y + 0.5f) / (float)N) - 1.0f;
-    return normalize_safe(face_to_dir(side, fx, fy));
-}
-
-__device__ __forceinline__ float ndf_ggx(float alphaSqr, float cosTheta) {
-    const float c = fminf(fmaxf(cosTheta, 0.0f), 1.0f);
-    const float d = (c * alphaSqr - c) * c + 1.0f;
-    // the reference divides by the double constant M_PI (c_src/cubemap.cu:180): keep that rounding
-    return (float)((double)alphaSqr / ((double)(d * d) * 3.14159265358979323846));
-}
 
 __global__ void mip_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int res_out, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -142,10 +111,7 @@ specular_kernel(int N, float roughness, float cutoff, const int4* __restrict__ b
                 const F3 L = texel_dir(x, y, s, N);
                 const float LdotV = dot(L, V);
                 if (LdotV < cutoff) continue;
-                const F3 Hh = normalize_safe(L + V);
-                const float wiDotN = fmaxf(LdotV, 0.0f);
-                const float VdotH = fmaxf(dot(V, Hh), 0.0f);
-                const float w = wiDotN * ndf_ggx(alphaSqr, VdotH) * pixel_area(x, y, N) / 4.0f;
+                const float w = specular_tap_weight(V, L, LdotV, alphaSqr, pixel_area(x, y, N));
                 const size_t t = ((size_t)(s * N + y) * N + x) * 3;
                 if (BACKWARD) {
                     atomicAdd(dcubemap + t + 0, grad.x * w);
@@ -187,8 +153,7 @@ diffuse_kernel(int N, const float* __restrict__ cubemap, float* __restrict__ out
         for (int y = 0; y < N; ++y)
             for (int x = 0; x < N; ++x) {
                 const F3 L = texel_dir(x, y, s, N);
-                const float costheta = fminf(fmaxf(dot(Nn, L), 0.0f), 0.999f);
-                const float w = costheta * pixel_area(x, y, N) / 3.141592f;
+                const float w = diffuse_tap_weight(Nn, L, pixel_area(x, y, N));
                 const size_t t = ((size_t)(s * N + y) * N + x) * 3;
                 if (BACKWARD) {
                     atomicAdd(dcubemap + t + 0, grad.x * w);

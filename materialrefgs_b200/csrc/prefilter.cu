@@ -1,0 +1,659 @@
+// prefilter.cu — EnvLight.build_mips as a CONSTANT SPARSE OPERATOR streamed from HBM.
+//
+// The reference rebuilds its GGX mip chain every training iteration (train_refnerf.py:1155-1163 ->
+// scene/light.py:72-86): per level one SpecularCubemapFwdKernel / BwdKernel launch
+// (scene/renderutils/c_src/cubemap.cu:248-354) in which every output texel walks the texels of its cone and
+// re-derives, per tap, two normalisations, four atanf and a double-precision division; the backward scatters
+// three float atomics per tap. None of that arithmetic depends on the cubemap: for a given (resolution,
+// roughness, cutoff) the prefilter is a fixed linear map  out = W * cube,  dcube = W^T * dout  with ~1.1e9
+// non-zeros for the 6x512^2 chain. B200 has the HBM to keep W resident (2 x 4.7 GB: one copy per orientation)
+// and the bandwidth to stream it in 0.7 ms, so:
+//   * plan build (once per key, like the reference's cached __ndfBounds, ops.py:428-443): the weights are
+//     evaluated with the reference's own expression order (prefilter_math.cuh) over the reference's own loop
+//     domain (its cached per-face bounds, including the non-conservative 16x16 tile culling), normalised by
+//     the reference-order weight sum, and laid out for the gather below;
+//   * apply (every step): ONE launch for all levels + the diffuse map. A warp owns a patch of destination
+//     texels: a PW x (32/PW * G) block of one face (PW = 32, 16 or 8 lanes wide; a lane owns G vertically
+//     adjacent texels), or 32 consecutive texels in memory order for odd resolutions. The patch's taps are a
+//     list of source-row segments; within a segment lane l reads source texels xs_l, xs_l+1, ... (adjacent
+//     lanes read adjacent texels, served by L1) and its private weight stream, stored [slot][g][lane]. The
+//     patch's whole weight stream is contiguous: one elected lane pulls it through a 3-stage ring of 2 KB
+//     cp.async.bulk copies (mbarrier completion, L2 evict-first), so ~128 KB per SM are in flight without
+//     holding registers and every weight crosses HBM exactly once. The block shape is chosen per level by the
+//     host from exact slot counts (narrow blocks waste fewer padded slots where the cone leaves a face);
+//   * backward = the same gather with the transposed operator (built from the same expressions with the roles
+//     of the two texels swapped, membership checked against the SOURCE texel's bounds): no atomics, no zero
+//     fill, deterministic.
+// Layout of a plan (all caller-owned device memory, sizes from the count pass):
+//   patch_seg_begin  int32 [patches+1]      segment range of a patch
+//   patch_slot_begin int32 [patches+1]      first weight row (of 32*G floats) of a patch
+//   seg_desc         int2  [segments]       (linear texel index of the source row's texel 0, slots)
+//   spans            u16   [segments][32]   first source x of every lane (shifted so xs + slots <= N)
+//   weights          f32   [rows][G][32]    zero where a lane's cone does not reach
+#include "kernels.cuh"
+#include "prefilter_math.cuh"
+
+namespace mrgs {
+
+namespace {
+
+constexpr int kSpecFwd = MRGS_PREFILTER_SPECULAR;
+constexpr int kSpecBwd = MRGS_PREFILTER_SPECULAR_T;
+constexpr int kDiffFwd = MRGS_PREFILTER_DIFFUSE;
+constexpr int kDiffBwd = MRGS_PREFILTER_DIFFUSE_T;
+
+__global__ void texel_table_kernel(int N, float4* __restrict__ tab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * N * N) return;
+    const int x = i % N, y = (i / N) % N, s = i / (N * N);
+    const F3 d = texel_dir(x, y, s, N);
+    tab[i] = make_float4(d.x, d.y, d.z, pixel_area(x, y, N));
+}
+
+// destination texel g of lane `lane` of patch `patch`. PWL = log2(patch width in lanes); PWL == 5 && G == 1 is the
+// linear layout (any N); otherwise the patch is a PW x (PH * G) block with PH = 32 / PW (N % PW == 0, N % (PH*G) == 0)
+template <int G>
+__device__ __forceinline__ int patch_texel(int patch, int lane, int g, int N, int pwl) {
+    if (G == 1 && pwl == 5) return patch * 32 + lane;
+    const int pw = 1 << pwl, ph = 32 >> pwl;
+    const int bx_count = N >> pwl;
+    const int by_count = N / (ph * G);
+    const int bx = patch % bx_count;
+    const int by = (patch / bx_count) % by_count;
+    const int face = patch / (bx_count * by_count);
+    const int lx = lane & (pw - 1), ly = lane >> pwl;
+    return (face * N + by * ph * G + ly * G + g) * N + (bx << pwl) + lx;
+}
+
+__device__ __forceinline__ int warp_max(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_min(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+struct BuildParams {
+    int N, texels, num_patches, full_search, pwl;
+    float cutoff, alphaSqr;
+    const float4* tab;
+    const int4* bounds;
+    const float* wsum;         // fill pass of kSpecFwd, both passes of kSpecBwd
+    int* seg_count;            // count pass
+    int* slot_count;
+    int* tap_count;
+    float* wsum_out;           // count pass of kSpecFwd
+    const int* patch_seg_begin;  // fill pass
+    const int* patch_slot_begin;
+    int2* seg_desc;
+    uint16_t* spans;
+    float* weights;
+};
+
+// is candidate texel b (direction/area B) a tap of lane texel a, and with which (un-normalised) weight?
+// kSpecFwd / kDiffFwd: a is the OUTPUT texel (V), b the source (L).  *Bwd: a is the SOURCE texel whose
+// gradient is gathered (L), b the output texel (V) - the reference visits the pair from b's loop, so b's bounds
+// decide (c_src/cubemap.cu:271-279).
+template <int KIND, bool WEIGHT>
+__device__ __forceinline__ bool tap(const BuildParams& p, float4 A, int xa, int ya, int fa, int ib, float4 B,
+                                    float& w) {
+    const F3 a = {A.x, A.y, A.z}, b = {B.x, B.y, B.z};
+    if (KIND == kSpecFwd) {
+        const float LdotV = dot(b, a);
+        if (!(LdotV >= p.cutoff)) return false;
+        if (WEIGHT) w = specular_tap_weight(a, b, LdotV, p.alphaSqr, B.w);
+        return true;
+    } else if (KIND == kSpecBwd) {
+        const float LdotV = dot(a, b);
+        if (!(LdotV >= p.cutoff)) return false;
+        const int4 bb = __ldg(p.bounds + (size_t)ib * 6 + fa);
+        if (!(bb.x <= xa && xa <= bb.y && bb.z <= ya && ya <= bb.w)) return false;
+        if (WEIGHT) w = specular_tap_weight(b, a, LdotV, p.alphaSqr, A.w) / __ldg(p.wsum + ib);
+        return true;
+    } else if (KIND == kDiffFwd) {
+        const float v = diffuse_tap_weight(a, b, B.w);
+        if (WEIGHT) w = v;
+        return v != 0.0f;
+    } else {
+        const float v = diffuse_tap_weight(b, a, A.w);
+        if (WEIGHT) w = v;
+        return v != 0.0f;
+    }
+}
+
+template <int KIND, int G, bool FILL>
+__global__ void __launch_bounds__(128) plan_build_kernel(const BuildParams p) {
+    const int patch = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (patch >= p.num_patches) return;
+    const int N = p.N;
+    int ia[G], xa[G], ya[G], fa[G];
+    bool valid[G];
+    float4 A[G];
+    float wsum[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        ia[g] = patch_texel<G>(patch, lane, g, N, p.pwl);
+        valid[g] = ia[g] < p.texels;
+        const int i = valid[g] ? ia[g] : 0;
+        xa[g] = i % N;
+        ya[g] = (i / N) % N;
+        fa[g] = i / (N * N);
+        A[g] = __ldg(p.tab + i);
+        wsum[g] = 0.0f;
+    }
+    constexpr bool kBoundsDomain = KIND == kSpecFwd || KIND == kSpecBwd;
+    const bool own_bounds = KIND == kSpecFwd || (KIND == kSpecBwd && !p.full_search);
+    int nseg = 0, nslot = 0, ntap = 0;
+    const int seg_base = FILL ? p.patch_seg_begin[patch] : 0;
+    const int slot_base = FILL ? p.patch_slot_begin[patch] : 0;
+
+    for (int s = 0; s < 6; ++s) {
+        int4 box[G];
+        bool has[G];
+        int ylo = 1 << 30, yhi = -1;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            box[g] = make_int4(0, N - 1, 0, N - 1);
+            if (kBoundsDomain && own_bounds && valid[g]) box[g] = __ldg(p.bounds + (size_t)ia[g] * 6 + s);
+            has[g] = valid[g] && box[g].x <= box[g].y;
+            if (has[g]) {
+                ylo = min(ylo, box[g].z);
+                yhi = max(yhi, box[g].w);
+            }
+        }
+        ylo = warp_min(ylo);
+        yhi = warp_max(yhi);
+        for (int y = ylo; y <= yhi; ++y) {
+            const int row_base = (s * N + y) * N;
+            int first = 1 << 30, last = -1;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+                if (!has[g] || y < box[g].z || y > box[g].w) continue;
+                for (int x = box[g].x; x <= box[g].y; ++x) {
+                    float w = 0.0f;
+                    const bool kNeedW = !FILL && KIND == kSpecFwd && p.wsum_out != nullptr;
+                    if (kNeedW ? tap<KIND, true>(p, A[g], xa[g], ya[g], fa[g], row_base + x, __ldg(p.tab + row_base + x), w)
+                               : tap<KIND, false>(p, A[g], xa[g], ya[g], fa[g], row_base + x, __ldg(p.tab + row_base + x), w)) {
+                        first = min(first, x);
+                        last = max(last, x);
+                        if (kNeedW) wsum[g] += w;   // s, y, x ascending: the reference's summation order
+                        ++ntap;
+                    }
+                }
+            }
+            const int len = last >= first ? last - first + 1 : 0;
+            const int slots = warp_max(len);
+            if (slots == 0) continue;
+            if (FILL) {
+                const int seg = seg_base + nseg;
+                const int xs = len > 0 ? min(first, N - slots) : 0;
+                if (lane == 0) p.seg_desc[seg] = make_int2(row_base, slots);
+                p.spans[(size_t)seg * 32 + lane] = (uint16_t)xs;
+                float* wrow = p.weights + ((size_t)(slot_base + nslot) * G) * 32 + lane;
+                for (int i = 0; i < slots; ++i) {
+                    const int x = xs + i;
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        float w = 0.0f;
+                        bool in = has[g] && y >= box[g].z && y <= box[g].w && x >= box[g].x && x <= box[g].y;
+                        if (in) in = tap<KIND, true>(p, A[g], xa[g], ya[g], fa[g], row_base + x, __ldg(p.tab + row_base + x), w);
+                        if (in && KIND == kSpecFwd) w = w / __ldg(p.wsum + ia[g]);
+                        wrow[((size_t)i * G + g) * 32] = in ? w : 0.0f;
+                    }
+                }
+            }
+            ++nseg;
+            nslot += slots;
+        }
+    }
+    if (!FILL) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ntap += __shfl_xor_sync(0xffffffffu, ntap, o);
+        if (lane == 0) {
+            p.seg_count[patch] = nseg;
+            p.slot_count[patch] = nslot;
+            p.tap_count[patch] = ntap;
+        }
+        if (KIND == kSpecFwd && p.wsum_out != nullptr) {
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+                if (valid[g]) p.wsum_out[ia[g]] = wsum[g];
+        }
+    }
+}
+
+template <int KIND, int G>
+void launch_build(const BuildParams& p, bool fill, cudaStream_t stream) {
+    const int blocks = (p.num_patches + 3) / 4;
+    if (fill)
+        plan_build_kernel<KIND, G, true><<<blocks, 128, 0, stream>>>(p);
+    else
+        plan_build_kernel<KIND, G, false><<<blocks, 128, 0, stream>>>(p);
+}
+
+// ---- apply ---------------------------------------------------------------------------------------
+constexpr int kMaxJobs = MRGS_PREFILTER_MAX_JOBS;
+constexpr int kGatherWarps = 8;
+constexpr int kStages = 3;            // ring depth per warp
+constexpr int kChunkFloats = 512;     // 2 KB per bulk copy = 16 weight rows (G = 1) / 8 (G = 2)
+constexpr int kRingFloats = kStages * kChunkFloats;
+constexpr size_t kGatherSmem = (size_t)kGatherWarps * (kRingFloats * sizeof(float) + kStages * sizeof(uint64_t));
+
+struct GatherJob {
+    const int* patch_seg_begin;
+    const int* patch_slot_begin;
+    const int2* seg_desc;
+    const uint16_t* spans;
+    const float* weights;
+    const float* src;
+    float* dst;
+    const float* nan_where_zero;
+    int N, G, pwl, texels, src_stride, dst_stride;
+};
+struct GatherParams {
+    GatherJob job[kMaxJobs];
+    int warp_end[kMaxJobs];
+    int num_jobs;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ uint64_t evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+// global -> shared bulk copy (TMA engine, no registers), completion counted in bytes on `bar`; read-once data
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(pol)
+        : "memory");
+}
+
+template <int SS>
+__device__ __forceinline__ F3 load_texel(const float* __restrict__ src, size_t idx) {
+    if (SS == 4) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src) + idx);
+        return {v.x, v.y, v.z};
+    }
+    const float* q = src + idx * 3;
+    return {__ldg(q), __ldg(q + 1), __ldg(q + 2)};
+}
+
+template <int G, int SS>
+__device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int lane, float* ring, uint64_t* bars) {
+    constexpr int kRowFloats = G * 32;
+    constexpr int kChunkRows = kChunkFloats / kRowFloats;
+    constexpr int kRingRows = kStages * kChunkRows;
+    constexpr int kBatch = 4;   // source texels per lane in flight per batch; two batches are in flight
+    int seg = __ldg(j.patch_seg_begin + patch);
+    const int seg_end = __ldg(j.patch_seg_begin + patch + 1);
+    const int row0 = __ldg(j.patch_slot_begin + patch);
+    const int total_rows = __ldg(j.patch_slot_begin + patch + 1) - row0;
+    const float* wsrc = j.weights + (size_t)row0 * kRowFloats;
+    const int nchunks = (total_rows + kChunkRows - 1) / kChunkRows;
+    const uint32_t ring_s = smem_u32(ring), bars_s = smem_u32(bars);
+    uint64_t pol = 0;
+    if (lane == 0) {
+        pol = evict_first_policy();
+#pragma unroll
+        for (int c = 0; c < kStages; ++c) {
+            if (c < nchunks) {
+                const uint32_t bytes = (uint32_t)min(kChunkRows, total_rows - c * kChunkRows) * kRowFloats * 4u;
+                mbar_expect_tx(bars_s + c * 8, bytes);
+                bulk_g2s(ring_s + c * kChunkFloats * 4, wsrc + (size_t)c * kChunkFloats, bytes, bars_s + c * 8, pol);
+            }
+        }
+    }
+    float acc[G][3];
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = acc[g][2] = 0.0f;
+
+    // segment cursor: (s0, rem) = next source texel of this lane and slots left in the current segment; the NEXT
+    // segment's descriptor is always in flight
+    int2 d_next = make_int2(0, 0);
+    unsigned xs_next = 0;
+    if (seg < seg_end) {
+        d_next = __ldg(j.seg_desc + seg);
+        xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
+    }
+    size_t s0 = 0;
+    int rem = 0;
+    auto next_batch = [&](F3 (&c)[kBatch]) -> int {   // loads up to kBatch source texels of ONE segment
+        if (rem == 0) {
+            if (seg >= seg_end) return 0;
+            s0 = (size_t)d_next.x + xs_next;
+            rem = d_next.y;
+            ++seg;
+            if (seg < seg_end) {
+                d_next = __ldg(j.seg_desc + seg);
+                xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
+            }
+        }
+        const int n = min(rem, kBatch);
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k)
+            if (k < n) c[k] = load_texel<SS>(j.src, s0 + k);
+        s0 += n;
+        rem -= n;
+        return n;
+    };
+
+    int r = 0;   // flat weight row of the patch = position in the ring modulo kRingRows
+    F3 cb[kBatch], cn[kBatch];
+    int nb = next_batch(cb);
+    while (nb > 0) {
+        const int nn = next_batch(cn);   // the following batch's loads are issued before this one is consumed
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) {
+            if (k < nb) {
+                const int q = r / kChunkRows;            // chunk of this row
+                const int stage = q % kStages;
+                if (r % kChunkRows == 0)                  // first row of a chunk: its copy must have landed
+                    while (!mbar_try_wait(bars_s + stage * 8, (uint32_t)(q / kStages) & 1u)) {}
+                const float* ws = ring + (r % kRingRows) * kRowFloats + lane;
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float wv = ws[g * 32];
+                    acc[g][0] = fmaf(wv, cb[k].x, acc[g][0]);
+                    acc[g][1] = fmaf(wv, cb[k].y, acc[g][1]);
+                    acc[g][2] = fmaf(wv, cb[k].z, acc[g][2]);
+                }
+                ++r;
+                if (r % kChunkRows == 0) {   // chunk consumed: hand its stage back to the copy engine
+                    __syncwarp();
+                    const int refill = q + kStages;
+                    if (lane == 0 && refill < nchunks) {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        const uint32_t bytes = (uint32_t)min(kChunkRows, total_rows - refill * kChunkRows) * kRowFloats * 4u;
+                        mbar_expect_tx(bars_s + stage * 8, bytes);
+                        bulk_g2s(ring_s + stage * kChunkFloats * 4, wsrc + (size_t)refill * kChunkFloats, bytes,
+                                 bars_s + stage * 8, pol);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < kBatch; ++k) cb[k] = cn[k];
+        nb = nn;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        const int o = patch_texel<G>(patch, lane, g, j.N, j.pwl);
+        if (o >= j.texels) continue;
+        float rr = acc[g][0], gg = acc[g][1], b = acc[g][2];
+        if (j.nan_where_zero != nullptr && __ldg(j.nan_where_zero + o) == 0.0f) {
+            // the reference divides by the weight sum: an empty cone yields 0/0 (c_src/cubemap.cu:296-299 + ops.py:458)
+            rr = gg = b = __int_as_float(0x7fc00000);
+        }
+        float* q = j.dst + (size_t)o * j.dst_stride;
+        q[0] = rr;
+        q[1] = gg;
+        q[2] = b;
+    }
+}
+
+__global__ void __launch_bounds__(kGatherWarps * 32, 4) prefilter_gather_kernel(const __grid_constant__ GatherParams p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    float* ring = reinterpret_cast<float*>(smem_raw) + wib * kRingFloats;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kGatherWarps * kRingFloats * sizeof(float)) + wib * kStages;
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < kStages; ++c) mbar_init(smem_u32(bars + c), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    const int warp = blockIdx.x * kGatherWarps + wib;
+    int k = 0, first = 0;
+    while (k < p.num_jobs && warp >= p.warp_end[k]) {
+        first = p.warp_end[k];
+        ++k;
+    }
+    if (k >= p.num_jobs) return;
+    const GatherJob& j = p.job[k];
+    const int patch = warp - first;
+    if (j.G == 1) {
+        if (j.src_stride == 4) gather_patch<1, 4>(j, patch, lane, ring, bars);
+        else gather_patch<1, 3>(j, patch, lane, ring, bars);
+    } else {
+        if (j.src_stride == 4) gather_patch<2, 4>(j, patch, lane, ring, bars);
+        else gather_patch<2, 3>(j, patch, lane, ring, bars);
+    }
+}
+
+// ---- mip pyramid -----------------------------------------------------------------------------------
+// One CTA per T x T tile of the input level (T = min(32, res)): loads the tile once, writes a float4-padded
+// copy of it (optional) and the k levels below it, each the 2x2 average of the previous one
+// (avg_pool2d, scene/light_utils.py:69-71: window sum in row-major order, then * 0.25).
+struct PyramidParams {
+    const float* in;
+    int in_stride;     // 3 or 4 floats per texel
+    int res, T, k;
+    float4* out[MRGS_MAX_MIP_LEVELS];   // out[0]: copy of the input level (may be null), out[j]: res >> j
+};
+
+__global__ void __launch_bounds__(256) mip_pyramid_kernel(const __grid_constant__ PyramidParams p) {
+    __shared__ float4 buf0[32 * 32];
+    __shared__ float4 buf1[16 * 16];
+    const int T = p.T;
+    const int tiles = p.res / T;
+    const int tx = blockIdx.x % tiles, ty = (blockIdx.x / tiles) % tiles, face = blockIdx.x / (tiles * tiles);
+    for (int i = threadIdx.x; i < T * T; i += blockDim.x) {
+        const int x = tx * T + (i % T), y = ty * T + (i / T);
+        const size_t t = ((size_t)face * p.res + y) * p.res + x;
+        float4 v;
+        if (p.in_stride == 4) {
+            v = __ldg(reinterpret_cast<const float4*>(p.in) + t);
+        } else {
+            const float* q = p.in + t * 3;
+            v = make_float4(__ldg(q), __ldg(q + 1), __ldg(q + 2), 0.0f);
+        }
+        buf0[i] = v;
+        if (p.out[0] != nullptr) p.out[0][t] = v;
+    }
+    __syncthreads();
+    int size = T;
+    for (int jl = 1; jl <= p.k; ++jl) {
+        const int prev = size;
+        size >>= 1;
+        const float4* s = (jl & 1) ? buf0 : buf1;
+        float4* d = (jl & 1) ? buf1 : buf0;
+        const int r = p.res >> jl;
+        for (int i = threadIdx.x; i < size * size; i += blockDim.x) {
+            const int x = i % size, y = i / size;
+            const float4 a = s[(2 * y) * prev + 2 * x], b = s[(2 * y) * prev + 2 * x + 1];
+            const float4 c = s[(2 * y + 1) * prev + 2 * x], e = s[(2 * y + 1) * prev + 2 * x + 1];
+            float4 v;
+            v.x = (a.x + b.x + c.x + e.x) * 0.25f;
+            v.y = (a.y + b.y + c.y + e.y) * 0.25f;
+            v.z = (a.z + b.z + c.z + e.z) * 0.25f;
+            v.w = 0.0f;
+            d[i] = v;
+            p.out[jl][((size_t)face * r + (ty * size + y)) * r + tx * size + x] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// g_fine += 0.25 * seamless bilinear fetch of (g_coarse [+ g_coarse2]) at the fine texel directions: the
+// reference's (non-adjoint) cubemap_mip backward, scene/light_utils.py:72-80, accumulated in place
+__global__ void mip_bwd_acc_kernel(const float* __restrict__ g_coarse, const float* __restrict__ g_coarse2,
+                                   float* __restrict__ g_fine, int res_coarse, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int rf = res_coarse * 2;
+    if (i >= 6 * rf * rf) return;
+    const int x = i % rf, y = (i / rf) % rf, s = i / (rf * rf);
+    const F3 d = texel_dir(x, y, s, rf);
+    const FaceUV f = dir_to_face(d);
+    Bilinear b;
+    cube_bilinear<false>(g_coarse, res_coarse, f.face, f.u, f.v, b);
+    F3 v = b.val;
+    if (g_coarse2 != nullptr) {
+        cube_bilinear<false>(g_coarse2, res_coarse, f.face, f.u, f.v, b);
+        v = v + b.val;
+    }
+    float* q = g_fine + 3 * (size_t)i;
+    if (accumulate) {
+        q[0] += 0.25f * v.x;
+        q[1] += 0.25f * v.y;
+        q[2] += 0.25f * v.z;
+    } else {
+        q[0] = 0.25f * v.x;
+        q[1] = 0.25f * v.y;
+        q[2] = 0.25f * v.z;
+    }
+}
+
+}  // namespace
+
+// ---- host side ---------------------------------------------------------------------------------------
+void launch_texel_table(int N, float* table, cudaStream_t stream) {
+    const int total = 6 * N * N;
+    texel_table_kernel<<<(total + 255) / 256, 256, 0, stream>>>(N, reinterpret_cast<float4*>(table));
+}
+
+static int log2_width(int pw) { return pw == 32 ? 5 : pw == 16 ? 4 : 3; }
+
+// -1 when the shape does not tile an N x N face
+int prefilter_patch_count(int N, int G, int PW) {
+    if (N < 1 || (G != 1 && G != 2) || (PW != 32 && PW != 16 && PW != 8)) return -1;
+    if (G == 1 && PW == 32) return (6 * N * N + 31) / 32;
+    const int ph = 32 / PW;
+    if (N % PW != 0 || N % (ph * G) != 0) return -1;
+    return 6 * (N / PW) * (N / (ph * G));
+}
+
+int launch_prefilter_build(const MrgsPrefilterBuildArgs* a, bool fill, cudaStream_t stream) {
+    BuildParams p;
+    p.N = a->res;
+    p.texels = 6 * a->res * a->res;
+    p.num_patches = prefilter_patch_count(a->res, a->rows_per_lane, a->patch_width);
+    p.full_search = a->full_search;
+    p.pwl = log2_width(a->patch_width);
+    p.cutoff = a->costheta_cutoff;
+    const float alpha = a->roughness * a->roughness;
+    p.alphaSqr = alpha * alpha;
+    p.tab = reinterpret_cast<const float4*>(a->texel_table);
+    p.bounds = reinterpret_cast<const int4*>(a->bounds);
+    p.wsum = a->wsum;
+    p.seg_count = a->seg_count;
+    p.slot_count = a->slot_count;
+    p.tap_count = a->tap_count;
+    p.wsum_out = a->kind == kSpecFwd ? a->wsum : nullptr;
+    p.patch_seg_begin = a->plan.patch_seg_begin;
+    p.patch_slot_begin = a->plan.patch_slot_begin;
+    p.seg_desc = reinterpret_cast<int2*>(a->plan.seg_desc);
+    p.spans = a->plan.spans;
+    p.weights = a->plan.weights;
+    const int G = a->rows_per_lane;
+#define MRGS_BUILD_CASE(K)                                   \
+    case K:                                                  \
+        if (G == 1) launch_build<K, 1>(p, fill, stream);     \
+        else launch_build<K, 2>(p, fill, stream);            \
+        break;
+    switch (a->kind) {
+        MRGS_BUILD_CASE(kSpecFwd)
+        MRGS_BUILD_CASE(kSpecBwd)
+        MRGS_BUILD_CASE(kDiffFwd)
+        MRGS_BUILD_CASE(kDiffBwd)
+        default:
+            return MRGS_ERR_INVALID_ARGUMENT;
+    }
+#undef MRGS_BUILD_CASE
+    return MRGS_OK;
+}
+
+int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, cudaStream_t stream) {
+    GatherParams p;
+    int warps = 0;
+    for (int k = 0; k < num_jobs; ++k) {
+        const MrgsPrefilterJob& s = jobs[k];
+        GatherJob& j = p.job[k];
+        j.patch_seg_begin = s.plan.patch_seg_begin;
+        j.patch_slot_begin = s.plan.patch_slot_begin;
+        j.seg_desc = reinterpret_cast<const int2*>(s.plan.seg_desc);
+        j.spans = s.plan.spans;
+        j.weights = s.plan.weights;
+        j.src = s.src;
+        j.dst = s.dst;
+        j.nan_where_zero = s.nan_where_zero;
+        j.N = s.plan.res;
+        j.G = s.plan.rows_per_lane;
+        j.pwl = log2_width(s.plan.patch_width);
+        j.texels = 6 * s.plan.res * s.plan.res;
+        j.src_stride = s.src_stride;
+        j.dst_stride = s.dst_stride;
+        warps += prefilter_patch_count(s.plan.res, s.plan.rows_per_lane, s.plan.patch_width);
+        p.warp_end[k] = warps;
+    }
+    p.num_jobs = num_jobs;
+    if (warps == 0) return MRGS_OK;
+    // > 48 KB of dynamic shared memory is an opt-in per device; setting it is cheap, so no per-process cache
+    if (cudaFuncSetAttribute(prefilter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem) !=
+        cudaSuccess)
+        return MRGS_ERR_CUDA;
+    prefilter_gather_kernel<<<(warps + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, kGatherSmem, stream>>>(p);
+    return MRGS_OK;
+}
+
+int launch_mip_pyramid(const float* base3, int res, int num_levels, float* const* levels4, cudaStream_t stream,
+                       int* launches) {
+    // levels handled per launch: log2(T) below the launch's input level
+    const float* in = base3;
+    int in_stride = 3, level = 0, r = res;
+    *launches = 0;
+    while (true) {
+        PyramidParams p;
+        p.in = in;
+        p.in_stride = in_stride;
+        p.res = r;
+        int lg = 0;   // T = the largest power of two dividing r, at most 32
+        while (lg < 5 && (r & ((2 << lg) - 1)) == 0) ++lg;
+        p.T = 1 << lg;
+        p.k = (num_levels - 1 - level) < lg ? (num_levels - 1 - level) : lg;
+        for (int j = 0; j < MRGS_MAX_MIP_LEVELS; ++j) p.out[j] = nullptr;
+        if (level == 0) p.out[0] = reinterpret_cast<float4*>(levels4[0]);
+        for (int j = 1; j <= p.k; ++j) p.out[j] = reinterpret_cast<float4*>(levels4[level + j]);
+        if (level > 0 && p.k == 0) break;
+        const int tiles = r / p.T;
+        mip_pyramid_kernel<<<6 * tiles * tiles, 256, 0, stream>>>(p);
+        ++*launches;
+        level += p.k;
+        if (level >= num_levels - 1 || p.k == 0) break;
+        in = levels4[level];
+        in_stride = 4;
+        r = res >> level;
+    }
+    return MRGS_OK;
+}
+
+void launch_mip_bwd_acc(const float* g_coarse, const float* g_coarse2, float* g_fine, int res_coarse, int accumulate,
+                        cudaStream_t stream) {
+    const int total = 6 * 4 * res_coarse * res_coarse;
+    mip_bwd_acc_kernel<<<(total + 255) / 256, 256, 0, stream>>>(g_coarse, g_coarse2, g_fine, res_coarse, accumulate);
+}
+
+}  // namespace mrgs

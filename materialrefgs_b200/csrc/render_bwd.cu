@@ -16,6 +16,8 @@
 //   * a warp skips the reduction when none of its pixels is touched by the instance.
 #include <cstdlib>
 
+#include <atomic>
+
 #include "kernels.cuh"
 #include "splat_math.cuh"
 
@@ -304,11 +306,17 @@ namespace {
 
 template <int NQ, int WPC, int MINB>
 void launch_variant(const RenderBwdParams& p, cudaStream_t stream) {
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(render_bwd_kernel<NQ, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             bwd_smem_bytes<NQ, WPC>());
-        configured = true;
+    // the attribute is per device: one flag per device (a process may drive several GPUs); set only when the
+    // variant needs more than the 48 KB every device grants by default
+    constexpr int kMaxDevices = 64;
+    static std::atomic<bool> configured[kMaxDevices];
+    int dev = 0;
+    if (bwd_smem_bytes<NQ, WPC>() > 48 * 1024 && cudaGetDevice(&dev) == cudaSuccess) {
+        if (dev < 0 || dev >= kMaxDevices || !configured[dev].load(std::memory_order_acquire)) {
+            cudaFuncSetAttribute(render_bwd_kernel<NQ, WPC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 bwd_smem_bytes<NQ, WPC>());
+            if (dev >= 0 && dev < kMaxDevices) configured[dev].store(true, std::memory_order_release);
+        }
     }
     const dim3 grid(p.grid_x, p.grid_y, kWarpsPerTile / WPC);
     render_bwd_kernel<NQ, WPC, MINB><<<grid, WPC * 32, bwd_smem_bytes<NQ, WPC>(), stream>>>(p);

@@ -1,5 +1,8 @@
 """Host-side mirror of the cubemap ops EnvLight.build_mips needs, backed by libmrgs.so.
 
+specular_cubemap / diffuse_cubemap apply a cached prefilter plan (prefilter.py: the op as a precomputed sparse
+operator, gather forward and backward); only plans beyond the HBM budget fall back to the direct per-texel kernels.
+
 Same names / argument meaning as the reference:
   cubemap_mip        scene/light_utils.py:66-80 (autograd.Function with the non-adjoint backward)
   diffuse_cubemap    scene/renderutils/ops.py:391-411
@@ -13,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from . import prefilter as pf
 
 
 def _stream(dev):
@@ -62,6 +66,27 @@ class _diffuse_cubemap(torch.autograd.Function):
     @staticmethod
     def forward(ctx, cubemap):
         _check_cube(cubemap, 3)
+        x = cubemap.contiguous()
+        fwd, bwd = pf.plan_pair("diffuse", x.shape[1], 0.0, None, x.device)
+        out = torch.empty_like(x)
+        pf.apply_jobs([(fwd, x, 3, out, 3, None)], False, x.device)
+        ctx.plan = bwd
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = dout.contiguous()
+        g = torch.empty_like(d)
+        pf.apply_jobs([(ctx.plan, d, 3, g, 3, None)], True, d.device)
+        return g
+
+
+class _diffuse_cubemap_direct(torch.autograd.Function):
+    """The per-texel loop kernels (cold path: maps too large for a plan)."""
+
+    @staticmethod
+    def forward(ctx, cubemap):
+        _check_cube(cubemap, 3)
         lib = _lib.load()
         x = cubemap.contiguous()
         out = torch.empty_like(x)
@@ -85,44 +110,72 @@ class _diffuse_cubemap(torch.autograd.Function):
 
 def diffuse_cubemap(cubemap, use_python=False):
     assert not use_python
+    _check_cube(cubemap, 3)
+    if pf.estimate_bytes(cubemap.shape[1], None) > pf.budget_bytes():
+        return _diffuse_cubemap_direct.apply(cubemap)
     return _diffuse_cubemap.apply(cubemap)
 
 
-def ndf_cutoff_costheta(roughness: float, cutoff: float) -> float:
-    """cos of the cone angle that keeps `cutoff` of the GGX lobe's energy: the host-side search of
-    __ndfBounds (scene/renderutils/ops.py:428-441), same 1e6-sample cumsum in float64."""
-    def ndfGGX(alphaSqr, costheta):
-        costheta = np.clip(costheta, 0.0, 1.0)
-        d = (costheta * alphaSqr - costheta) * costheta + 1.0
-        return alphaSqr / (d * d * np.pi)
-    nSamples = 1000000
-    costheta = np.cos(np.linspace(0, np.pi / 2.0, nSamples))
-    D = np.cumsum(ndfGGX(roughness ** 4, costheta))
-    idx = np.argmax(D >= D[..., -1] * cutoff)
-    return float(costheta[idx])
-
+ndf_cutoff_costheta = pf.ndf_cutoff_costheta
+specular_bounds = pf.specular_bounds
 
 _bounds_cache: dict = {}
-
-
-def specular_bounds(res: int, costheta_cutoff: float, device) -> torch.Tensor:
-    lib = _lib.load()
-    bounds = torch.empty((6, res, res, 6, 4), dtype=torch.int32, device=device)
-    with torch.cuda.device(device):
-        _lib.check(lib.mrgs_specular_bounds(res, float(costheta_cutoff), bounds.data_ptr(), _stream(device)),
-                   "mrgs_specular_bounds")
-    return bounds
 
 
 def _ndf_bounds(res, roughness, cutoff, device):
     key = (res, roughness, cutoff, str(device))
     if key not in _bounds_cache:
-        ct = ndf_cutoff_costheta(roughness, cutoff)
+        ct = pf.cutoff_costheta(roughness, cutoff)
         _bounds_cache[key] = (ct, specular_bounds(res, ct, device))
     return _bounds_cache[key]
 
 
 class _specular_cubemap(torch.autograd.Function):
+    """The plugin-level op pair specular_cubemap_fwd / _bwd (scene/renderutils/ops.py:413-426): out4 = (sum w rgb,
+    sum w). `bounds` is accepted for signature parity; the plan derives the same bounds itself."""
+
+    @staticmethod
+    def forward(ctx, cubemap, roughness, costheta_cutoff, bounds):
+        x = cubemap.contiguous()
+        res = x.shape[1]
+        fwd, bwd = pf.plan_pair("specular", res, float(roughness), float(costheta_cutoff), x.device)
+        rgb = torch.empty_like(x)
+        pf.apply_jobs([(fwd, x, 3, rgb, 3, None)], False, x.device)
+        wsum = fwd.wsum.view(6, res, res, 1)
+        ctx.plan, ctx.wsum = bwd, wsum
+        return torch.cat([rgb * wsum, wsum], dim=-1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = (dout[..., :3] * ctx.wsum).contiguous()     # the plan's weights carry 1 / wsum
+        g = torch.empty_like(d)
+        pf.apply_jobs([(ctx.plan, d, 3, g, 3, None)], True, d.device)
+        return g, None, None, None
+
+
+class _specular_cubemap_normalised(torch.autograd.Function):
+    """specular_cubemap incl. the division by the weight sum (ops.py:445-458) as one gather each way."""
+
+    @staticmethod
+    def forward(ctx, cubemap, roughness, costheta_cutoff):
+        x = cubemap.contiguous()
+        fwd, bwd = pf.plan_pair("specular", x.shape[1], float(roughness), float(costheta_cutoff), x.device)
+        rgb = torch.empty_like(x)
+        pf.apply_jobs([(fwd, x, 3, rgb, 3, fwd.wsum)], False, x.device)
+        ctx.plan = bwd
+        return rgb
+
+    @staticmethod
+    def backward(ctx, dout):
+        d = dout.contiguous()
+        g = torch.empty_like(d)
+        pf.apply_jobs([(ctx.plan, d, 3, g, 3, None)], True, d.device)
+        return g, None, None
+
+
+class _specular_cubemap_direct(torch.autograd.Function):
+    """The per-texel cone-loop kernels (cold path: cones too large for a plan)."""
+
     @staticmethod
     def forward(ctx, cubemap, roughness, costheta_cutoff, bounds):
         lib = _lib.load()
@@ -153,6 +206,10 @@ class _specular_cubemap(torch.autograd.Function):
 def specular_cubemap(cubemap, roughness, cutoff=0.99, use_python=False):
     assert not use_python
     _check_cube(cubemap, 3)
-    ct, bounds = _ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device)
-    out = _specular_cubemap.apply(cubemap, roughness, ct, bounds)
-    return out[..., 0:3] / out[..., 3:]
+    ct = pf.cutoff_costheta(roughness, cutoff)
+    try:
+        return _specular_cubemap_normalised.apply(cubemap, roughness, ct)
+    except pf.PrefilterTooLarge:
+        ct, bounds = _ndf_bounds(cubemap.shape[1], roughness, cutoff, cubemap.device)
+        out = _specular_cubemap_direct.apply(cubemap, roughness, ct, bounds)
+        return out[..., 0:3] / out[..., 3:]

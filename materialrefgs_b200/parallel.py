@@ -42,26 +42,40 @@ class GradArena:
     views: Dict[str, torch.Tensor]
     stats: torch.Tensor
     max_radii: torch.Tensor
+    extra: torch.Tensor = None     # optional tail summed by the same collective (EnvLight's texel-gradient sink)
 
     @staticmethod
-    def create(P: int, device, fields: Sequence = GRAD_FIELDS) -> "GradArena":
+    def create(P: int, device, fields: Sequence = GRAD_FIELDS, extra_floats: int = 0) -> "GradArena":
+        """extra_floats: further fp32 values at the END of the same flat buffer (after a 16-byte aligned offset), e.g.
+        4 * texels for the environment map's [texels, 4] gradient sink (EnvLight.use_level_grad_sink), so that ONE
+        sum-allreduce covers per-surfel gradients, densification statistics and the cubemap gradients."""
         F = sum(w for _, w in fields)
-        flat = torch.zeros((P * (F + 2),), dtype=torch.float32, device=device)
+        main = P * (F + 2)
+        pad = (-main) % 4
+        flat = torch.zeros((main + pad + extra_floats,), dtype=torch.float32, device=device)
         views, o = {}, 0
         for name, w in fields:
             views[name] = flat[o:o + P * w].view(P, w)
             o += P * w
         return GradArena(flat, views, flat[o:o + 2 * P].view(P, 2),
-                         torch.zeros((P,), dtype=torch.int32, device=device))
+                         torch.zeros((P,), dtype=torch.int32, device=device),
+                         flat[main + pad:] if extra_floats else None)
+
+    @property
+    def main(self) -> torch.Tensor:
+        """Gradients + statistics (everything but the extra tail), 1-D."""
+        return self.flat if self.extra is None else self.flat[:self.flat.numel() - self.extra.numel()]
 
     @property
     def grads(self) -> torch.Tensor:
-        """The gradient part of the buffer (without the statistics tail), 1-D."""
-        return self.flat[:self.flat.numel() - self.stats.numel()]
+        """The gradient part of the buffer (without the statistics and the extra tail), 1-D."""
+        return self.main[:self.main.numel() - self.stats.numel()]
 
     def zero_(self):
         self.flat.zero_()
         self.max_radii.zero_()
+        if self.extra is not None:       # (the sink's owner tracks "holds unflushed gradients" on the tensor)
+            self.extra._mrgs_pending = False
 
     def bind(self, leaves: Dict[str, torch.Tensor]):
         """Make each parameter's .grad a view of its arena segment (call once; zero_() per step).
@@ -107,10 +121,37 @@ class GradArena:
         6 x 512^2: EnvLight.level_grad_sink)."""
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)     # incl. the extra tail, if any
         for t in extra:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group)
+
+    # ---- the same exchange in two overlappable pieces -------------------------------------------------------
+    # The extra tail (cubemap texel gradients) is complete as soon as the LAST view's shading backward is enqueued,
+    # i.e. before that view's rasterizer backward: its allreduce can run under those kernels. The main part is
+    # complete after the last per-surfel backward; its allreduce can run under the build_mips backward, which
+    # only consumes the (already reduced) tail. NCCL work is enqueued on NCCL's own stream, ordered after
+    # everything enqueued so far on the current stream; wait() orders the current stream after the collective.
+    @staticmethod
+    def _active(group) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+
+    def allreduce_extra_async(self, group=None):
+        if not self._active(group) or self.extra is None:
+            return None
+        return dist.all_reduce(self.extra, op=dist.ReduceOp.SUM, group=group, async_op=True)
+
+    def allreduce_main_async(self, group=None):
+        if not self._active(group):
+            return None
+        return [dist.all_reduce(self.main, op=dist.ReduceOp.SUM, group=group, async_op=True),
+                dist.all_reduce(self.max_radii, op=dist.ReduceOp.MAX, group=group, async_op=True)]
+
+    @staticmethod
+    def wait(work):
+        for w in (work if isinstance(work, (list, tuple)) else [work]):
+            if w is not None:
+                w.wait()
 
 
 def train_step_view_sharded(render_view: Callable[[int], Dict], n_views: int, arena: GradArena,

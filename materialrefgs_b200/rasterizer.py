@@ -140,6 +140,7 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.mrgs_forward(C.byref(a), C.c_void_p(stream)), "mrgs_forward")
     R = int(a.num_rendered)
+    _last_num_rendered[dev.index] = R
     binning = holder.get("t")
     if binning is None:
         binning = scratch if (scratch is not None and a.binning_buffer == scratch.data_ptr()) else \
@@ -150,6 +151,9 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
         if want > cap:
             _capacity_hint[dev.index] = want
     return R, contrib, color, feature, others, radii, geom, binning, image
+
+
+_last_num_rendered: dict = {}
 
 
 def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales, rotations,
@@ -363,5 +367,8 @@ class GaussianRasterizer(nn.Module):
             rotations = empty()
         if cov3D_precomp is None:
             cov3D_precomp = empty()
-        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales,
-                                   rotations, cov3D_precomp, rs, self.grad_sink)
+        out = rasterize_gaussians(means3D, means2D, shs, colors_precomp, features, opacities, scales,
+                                  rotations, cov3D_precomp, rs, self.grad_sink)
+        # instances (tile, surfel) of this view, already on the host (the reference's `rendered`): a free cost estimate
+        self.num_rendered = _last_num_rendered.get(means3D.device.index)
+        return out

@@ -94,9 +94,12 @@ def render_surfel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_mo
         means3D=means3D, means2D=screenspace_points, shs=shs, colors_precomp=colors_precomp, features=features,
         opacities=opacity, scales=scales, rotations=rotations, cov3D_precomp=None)
 
-    surf_depth, surf_normal = surf_depth_normal(allmap, imH, imW, tanfovx, tanfovy, viewpoint_camera.R,
-                                                viewpoint_camera.T, getattr(pipe, "depth_ratio", 0.0))
     if wo_render_img:
+        # the reference skips depth_to_normal here (return_depth_normal=False, gaussian_renderer/__init__.py:388,
+        # :71-77): surf_normal is None and only the depth mix of :50-70 is evaluated
+        ratio = getattr(pipe, "depth_ratio", 0.0)
+        surf_depth = torch.nan_to_num(allmap[0:1] / allmap[1:2], 0, 0) * (1 - ratio) + ratio * torch.nan_to_num(allmap[5:6], 0, 0)
+        surf_normal = None
         w2v_rot = viewpoint_camera.world_view_transform[:3, :3]
         render_normal = (allmap[2:5].permute(1, 2, 0) @ w2v_rot.T).permute(2, 0, 1)
         return {"refl_strength_map": rendered_features[:1], "base_color_map": rendered_features[2:5],
@@ -105,6 +108,8 @@ def render_surfel(viewpoint_camera, pc, pipe, bg_color: torch.Tensor, scaling_mo
                 "rend_normal": render_normal, "rend_dist": allmap[6:7], "surf_depth": surf_depth,
                 "surf_normal": surf_normal}
 
+    surf_depth, surf_normal = surf_depth_normal(allmap, imH, imW, tanfovx, tanfovy, viewpoint_camera.R,
+                                                viewpoint_camera.T, getattr(pipe, "depth_ratio", 0.0))
     maps = shade_surfel(pc.get_envmap, rendered_image, rendered_features, allmap, viewpoint_camera.HWK,
                         viewpoint_camera.R, bg_color, srgb=srgb)
     albedo, specular = maps["base_color_map"], maps["specular_map"]

@@ -138,6 +138,11 @@ class _ShadeSurfel(torch.autograd.Function):
             off += n
         with torch.cuda.device(dev):
             _lib.check(lib.mrgs_shade_backward(C.byref(a), _stream(dev)), "mrgs_shade_backward")
+        if sink is not None:
+            sink._mrgs_pending = True
+            hook = getattr(ctx.cfg[6], "after_sink_backward", None) if len(ctx.cfg) > 6 else None
+            if hook is not None:        # e.g. start the sink's allreduce under the rasterizer backward that follows
+                hook()
         if sink is not None or flat4 is None:    # the sink owns the texel gradients (EnvLight.flush_level_grads)
             return (d_base, d_feat, d_allmap, None, None, *([None] * len(levels)))
         flat3 = flat4[:, :3].contiguous()
@@ -208,7 +213,7 @@ def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, 
     (gaussian_renderer/__init__.py:372-469). HWK = (H, W, K) and R (c2w rotation) come from the
     camera exactly as the reference passes `viewpoint_camera.HWK / .R`."""
     cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb,
-           getattr(envmap, "level_grad_sink", None))
+           getattr(envmap, "level_grad_sink", None), envmap)
     final, specular, direct, normal_w, diffuse = _ShadeSurfel.apply(
         rendered_image, rendered_features, allmap, bg_color, cfg, *envmap.specular)
     return {
@@ -381,50 +386,102 @@ class EnvLight(torch.nn.Module):
             requires_grad=trainable)
         self.build_mips()
 
+    _chain = None
+
+    def chain_roughnesses(self, n):
+        """Roughness of every level as build_mips assigns them (scene/light.py:81-86)."""
+        return [(idx / (n - 2)) * (self.max_roughness - self.min_roughness) + self.min_roughness
+                for idx in range(n - 1)] + [1.0]
+
     def build_mips(self, cutoff=0.99):
+        """scene/light.py:72-86. Power-of-two chains run as ONE autograd node over cached prefilter plans
+        (prefilter.py: mip pyramid + one gather launch forward, one gather + the mip backward chain backward);
+        other shapes, and chains whose plans exceed the HBM budget, compose the per-level ops like the reference."""
         from . import cubemap as cm
-        self.specular = [self.base]
-        while self.specular[-1].shape[1] > self.min_res:
-            self.specular += [cm.cubemap_mip(self.specular[-1])]
-        self.diffuse = cm.diffuse_cubemap(self.specular[-1])
-        n = len(self.specular)
-        for idx in range(n - 1):
-            roughness = (idx / (n - 2)) * (self.max_roughness - self.min_roughness) + self.min_roughness
-            self.specular[idx] = cm.specular_cubemap(self.specular[idx], roughness, cutoff)
-        self.specular[-1] = cm.specular_cubemap(self.specular[-1], 1.0, cutoff)
+        from . import prefilter as pf
+        sink = self.level_grad_sink
+        if sink is not None and getattr(sink, "_mrgs_pending", False):
+            raise RuntimeError("EnvLight.build_mips(): the level-gradient sink holds gradients of the previous chain; "
+                               "call flush_level_grads() first")
+        n, r = 1, self.max_res
+        while r > self.min_res:
+            r //= 2
+            n += 1
+        self._chain = None
+        if self.base.is_cuda and n != 2 and n <= _lib.MAX_MIP_LEVELS and self.max_res % (1 << (n - 1)) == 0:
+            try:
+                self._chain = pf.get_chain(self.max_res, n, self.chain_roughnesses(n), cutoff, self.base.device)
+            except pf.PrefilterTooLarge:
+                self._chain = None
+        if self._chain is not None:
+            self.specular, self.diffuse = pf.build_mips(self.base, self._chain)
+        else:
+            self.specular = [self.base]
+            while self.specular[-1].shape[1] > self.min_res:
+                self.specular += [cm.cubemap_mip(self.specular[-1])]
+            self.diffuse = cm.diffuse_cubemap(self.specular[-1])
+            n = len(self.specular)
+            for idx in range(n - 1):
+                roughness = (idx / (n - 2)) * (self.max_roughness - self.min_roughness) + self.min_roughness
+                self.specular[idx] = cm.specular_cubemap(self.specular[idx], roughness, cutoff)
+            self.specular[-1] = cm.specular_cubemap(self.specular[-1], 1.0, cutoff)
+        if sink is not None:
+            self.enable_level_grad_sink()     # re-sized if the chain's texel count changed
 
     def set_chain(self, levels):
         """Install an externally built mip chain (tests / benchmarks)."""
         self.specular = list(levels)
+        self._chain = None
 
     level_grad_sink = None
 
     def enable_level_grad_sink(self):
         """Multi-view steps: let the shading backward ADD the texel gradients of every view into ONE persistent
         [texels, 4] buffer instead of returning them through autograd (per view that costs a zero-fill of the buffer, a
-        strided copy to [.,3] and one accumulation pass per level). Call flush_level_grads() once per step: it feeds the
-        summed gradients into the mip chain's autograd graph (or the levels' .grad when they are leaves) and clears the
-        buffer. Gradients are linear in the upstream gradient, so the result equals per-view accumulation."""
+        strided copy to [.,3] and one accumulation pass per level). Call flush_level_grads() once per step, before the
+        next build_mips(): with a fused chain it runs the prefilter backward straight from the buffer into `base.grad`
+        (no autograd graph involved, so chains that were ALSO differentiated through autograd in the same step simply
+        add up in `base.grad`); otherwise it feeds the sums into the levels' autograd graph (which must then not have
+        been freed by an earlier backward) or the levels' .grad when they are leaves. The sink serves shade_surfel
+        only; EnvLight.__call__ and the per-surfel shading return their texel gradients through autograd."""
         n = sum(l.shape[0] * l.shape[1] * l.shape[2] for l in self.specular)
         dev = self.specular[0].device
         if self.level_grad_sink is None or self.level_grad_sink.shape[0] != n or self.level_grad_sink.device != dev:
             self.level_grad_sink = torch.zeros((n, 4), dtype=torch.float32, device=dev)
         return self.level_grad_sink
 
+    after_sink_backward = None     # optional callable, run right after a shading backward has added into the sink
+
+    def use_level_grad_sink(self, buffer):
+        """Adopt a caller-owned [texels, 4] fp32 buffer as the sink (e.g. the tail of parallel.GradArena's flat buffer, so
+        that one allreduce carries the surfel gradients and the cubemap gradients)."""
+        n = sum(l.shape[0] * l.shape[1] * l.shape[2] for l in self.specular)
+        if tuple(buffer.shape) != (n, 4) or buffer.dtype != torch.float32 or not buffer.is_contiguous() or \
+                buffer.device != self.specular[0].device:
+            raise RuntimeError(f"level-gradient sink must be a contiguous float32 [{n}, 4] tensor on {self.specular[0].device}")
+        self.level_grad_sink = buffer
+        return buffer
+
     def flush_level_grads(self):
         sink = self.level_grad_sink
         if sink is None:
             return
-        flat3 = sink[:, :3].contiguous()
-        grads, off = [], 0
-        for l in self.specular:
-            n = l.shape[0] * l.shape[1] * l.shape[2]
-            grads.append(flat3[off:off + n].view(l.shape))
-            off += n
-        live = [(l, g) for l, g in zip(self.specular, grads) if l.requires_grad]
-        if live:
-            torch.autograd.backward([l for l, _ in live], grad_tensors=[g for _, g in live])
+        if self._chain is not None:
+            if self.base.requires_grad:
+                g = self._chain.backward(sink, None)
+                self.base.grad = g if self.base.grad is None else self.base.grad.add_(g)
+        else:
+            flat3 = sink[:, :3].contiguous()
+            grads, off = [], 0
+            for l in self.specular:
+                n = l.shape[0] * l.shape[1] * l.shape[2]
+                grads.append(flat3[off:off + n].view(l.shape))
+                off += n
+            live = [(l, g) for l, g in zip(self.specular, grads) if l.requires_grad]
+            if live:
+                torch.autograd.backward([l for l, _ in live], grad_tensors=[g for _, g in live])
         sink.zero_()
+        sink._mrgs_pending = False
 
     def get_mip(self, roughness):
         n = len(self.specular)
@@ -502,22 +559,3 @@ class _EnvQuery(torch.autograd.Function):
             g_levels.append(flat4[off:off + n, :3].reshape(x.shape) if need else None)
             off += n
         return (g_d, g_r, None, *g_levels)
-
-
-def smoke_check(dev) -> None:
-    """Tiny forward+backward of the fused shader against the torch restatement (used by smoke())."""
-    from materialrefgs_b200 import synthetic
-    from oracle import shading_oracle as so
-    H, W = 64, 96
-    cam = synthetic.orbit_camera(1, 8, W, H)
-    base, feats, allmap = so.synthetic_gbuffer(H, W, device="cpu")
-    levels = so.synthetic_chain(64, 16)
-    bg = torch.tensor([0.2, 0.4, 0.6])
-    ref = so.shade_surfel(so.EnvLightOracle(levels), so.load_lut(), base, feats, allmap, cam, bg)
-    env = EnvLight.__new__(EnvLight)
-    torch.nn.Module.__init__(env)
-    env.min_roughness, env.max_roughness = 0.08, 0.5
-    env.set_chain([l.to(dev) for l in levels])
-    out = shade_surfel(env, base.to(dev), feats.to(dev), allmap.to(dev), cam.HWK, cam.R, bg.to(dev))
-    err = (out["render"].cpu() - ref["render"]).abs().max().item()
-    assert err <= 1e-4, f"fused shading differs from the oracle by {err}"

@@ -25,6 +25,12 @@ import torch
 from torch import nn
 
 
+# optimizer group order of the reference's training_setup (gaussian_model.py:422-447); "env"/"env2" are the two EnvLight
+# modules' parameters, which live outside this store
+REFERENCE_GROUP_ORDER = ("xyz", "f_dc", "f_rest", "opacity", "scaling", "rotation", "env", "env2", "refl_strength", "ori_color",
+                         "diffuse_color", "roughness", "metalness", "normal1", "normal2", "ind_dc", "ind_rest", "ind_asg")
+
+
 @dataclass(frozen=True)
 class Field:
     group: str            # optimizer group name (gaussian_model.py:422-447)
@@ -445,9 +451,42 @@ class SurfelStore:
             self.active_sh_degree += 1
 
     # -- checkpoint tuple (gaussian_model.py:124-172); train_refnerf.py saves torch.save((capture(), iteration), path)
-    def capture(self):
+    def reference_optimizer_state(self, env_groups: dict | None = None) -> dict:
+        """An Adam state dict laid out like the reference's optimizer (training_setup, gaussian_model.py:422-447): its 18
+        groups in ITS order — the reference's restore() loads the dict positionally (:170) — including the two
+        environment-map groups this store does not own. Those come from `env_groups` ({"env": (group_dict, [state per
+        parameter]), "env2": ...}; group_dict = the param-group hyper-parameters without "params") or, failing that, from
+        what restore() read out of a reference checkpoint. Without them the dict would mis-assign every moment, so that
+        case raises instead of writing a checkpoint the reference silently loads wrongly."""
+        own = {g["name"]: g for g in self.optimizer.param_groups}
+        foreign = dict(getattr(self, "_foreign_groups", {}))
+        foreign.update(env_groups or {})
+        groups, state, idx = [], {}, 0
+        for name in REFERENCE_GROUP_ORDER:
+            if name in own:
+                g = own[name]
+                hyper = {k: v for k, v in g.items() if k != "params"}
+                states = [self.optimizer.state.get(p) for p in g["params"]]
+            elif name in foreign:
+                hyper, states = foreign[name]
+                hyper = dict(hyper)
+            else:
+                raise ValueError(f"capture(): optimizer group {name!r} is neither owned by the store nor supplied through "
+                                 "env_groups; the reference loads optimizer state positionally and needs all 18 groups")
+            hyper["params"] = list(range(idx, idx + len(states)))
+            for k, st in enumerate(states):
+                if st:
+                    state[idx + k] = {a: (b.detach().clone() if isinstance(b, torch.Tensor) else b) for a, b in st.items()}
+            idx += len(states)
+            groups.append(hyper)
+        return {"state": state, "param_groups": groups}
+
+    def capture(self, env_groups: dict | None = None):
+        """The reference's checkpoint tuple (gaussian_model.py:124-148) with the optimizer state in the reference's group
+        layout (see reference_optimizer_state): `torch.save((store.capture(), iteration), path)` is loadable by the
+        reference's restore()."""
         return (self.active_sh_degree, *[self.params[n] for n in _CAPTURE_ORDER], self.max_radii2D,
-                self.xyz_gradient_accum, self.denom, self.optimizer.state_dict(), self.spatial_lr_scale)
+                self.xyz_gradient_accum, self.denom, self.reference_optimizer_state(env_groups), self.spatial_lr_scale)
 
     @classmethod
     def restore(cls, model_args, lrs: dict | None = None, device=None, **kw):
@@ -468,6 +507,10 @@ class SurfelStore:
         # the reference's optimizer also holds the two environment maps (groups "env", "env2"): take the per-surfel
         # groups by NAME, whatever their position in the saved state dict
         by_name = {g["name"]: g for g in opt_dict["param_groups"]}
+        own_names = {g["name"] for g in st.optimizer.param_groups}
+        st._foreign_groups = {      # kept so that capture() can write them back where the reference expects them
+            n: ({k: v for k, v in g.items() if k != "params"}, [opt_dict["state"].get(i) for i in g["params"]])
+            for n, g in by_name.items() if n not in own_names}
         for group in st.optimizer.param_groups:
             saved = by_name.get(group["name"])
             if saved is None:

@@ -161,6 +161,33 @@ def test_restore_reads_a_checkpoint_written_by_the_reference():
     assert len(again) == 22 and again[0] == 2 and again[21] == 3.5
     for i, n in enumerate(names):
         assert again[1 + i] is st[n]
+    # capture() writes the optimizer state in the REFERENCE's layout: an optimizer built like training_setup
+    # (gaussian_model.py:422-447: 18 groups, env/env2 in 7th/8th place) loads it positionally, moments on the right tensors
+    opt2 = again[20]
+    assert [g["name"] for g in opt2["param_groups"]] == [g["name"] for g in opt["param_groups"]] == list(sm.REFERENCE_GROUP_ORDER)
+    by_group = {f.group: [torch.nn.Parameter(st[n].detach().clone())] for n, f in sm.FIELDS.items()}
+    for n in ("env", "env2"):                          # as many parameters as the saved EnvLight module had
+        by_group[n] = [torch.nn.Parameter(torch.zeros(6, 4, 4, 3)) for _ in by_name[n]["params"]]
+    like_ref = torch.optim.Adam([{"params": by_group[n], "lr": 0.0, "name": n} for n in sm.REFERENCE_GROUP_ORDER], lr=0.0, eps=1e-15)
+    like_ref.load_state_dict(opt2)
+    for n, f in sm.FIELDS.items():
+        mine = st.optimizer.state.get(st[n])
+        theirs = like_ref.state.get(by_group[f.group][0])
+        assert (mine is None or not mine) == (theirs is None or not theirs), n
+        if mine:
+            assert torch.equal(mine["exp_avg"], theirs["exp_avg"]) and torch.equal(mine["exp_avg_sq"], theirs["exp_avg_sq"]), n
+    for n in ("env", "env2"):                          # carried through restore() -> capture() untouched
+        for k, i in enumerate(by_name[n]["params"]):
+            src, dst = opt["state"].get(i), like_ref.state.get(by_group[n][k])
+            assert (not src) == (not dst)
+            if src:
+                assert torch.equal(src["exp_avg"], dst["exp_avg"])
+    # a store that never saw the environment-map groups cannot write a reference-loadable tuple: it says so
+    fresh = sm.SurfelStore({n: st[n].detach().clone() for n in sm.FIELDS})
+    with pytest.raises(ValueError):
+        fresh.capture()
+    hyper = {k: v for k, v in by_name["env"].items() if k != "params"}
+    assert len(fresh.capture(env_groups={"env": (hyper, [None]), "env2": (dict(hyper, name="env2"), [None])})[20]["param_groups"]) == 18
     # the restored optimizer steps
     for p in st.params.values():
         p.grad = torch.ones_like(p)
