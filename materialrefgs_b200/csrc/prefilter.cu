@@ -30,6 +30,8 @@
 //   seg_desc         int2  [segments]       (linear texel index of the source row's texel 0, slots)
 //   spans            u16   [segments][32]   first source x of every lane (shifted so xs + slots <= N)
 //   weights          f32   [rows][G][32]    zero where a lane's cone does not reach
+#include <cstdlib>
+
 #include "kernels.cuh"
 #include "prefilter_math.cuh"
 
@@ -305,8 +307,6 @@ template <int G, int SS>
 __device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int lane, float* ring, uint64_t* bars) {
     constexpr int kRowFloats = G * 32;
     constexpr int kChunkRows = kChunkFloats / kRowFloats;
-    constexpr int kRingRows = kStages * kChunkRows;
-    constexpr int kBatch = 4;   // source texels per lane in flight per batch; two batches are in flight
     int seg = __ldg(j.patch_seg_begin + patch);
     const int seg_end = __ldg(j.patch_seg_begin + patch + 1);
     const int row0 = __ldg(j.patch_slot_begin + patch);
@@ -329,92 +329,100 @@ __device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int 
     float acc[G][3];
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g][0] = acc[g][1] = acc[g][2] = 0.0f;
-
-    // segment cursor: (s0, rem) = next source texel of this lane and slots left in the current segment; the NEXT
-    // segment's descriptor is always in flight
     int2 d_next = make_int2(0, 0);
     unsigned xs_next = 0;
     if (seg < seg_end) {
         d_next = __ldg(j.seg_desc + seg);
         xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
     }
-    size_t s0 = 0;
-    int rem = 0;
-    auto next_batch = [&](F3 (&c)[kBatch]) -> int {   // loads up to kBatch source texels of ONE segment
-        if (rem == 0) {
-            if (seg >= seg_end) return 0;
-            s0 = (size_t)d_next.x + xs_next;
-            rem = d_next.y;
-            ++seg;
-            if (seg < seg_end) {
-                d_next = __ldg(j.seg_desc + seg);
-                xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
-            }
+    int chunk = 0, stage = 0, rpos = 0;
+    uint32_t parity = 0;
+    if (nchunks > 0)
+        while (!mbar_try_wait(bars_s, 0)) {}
+    // Measured alternatives (profiles/r02_prefilter.md): issuing the NEXT batch's source loads before consuming the
+    // current one (two batches in flight, 64-72 registers) was 15 % slower than this plain 4-deep batch at 60 registers.
+    while (seg < seg_end) {
+        const int2 d = d_next;
+        size_t s0 = (size_t)d.x + xs_next;
+        ++seg;
+        if (seg < seg_end) {   // the next segment's descriptor is in flight while this one is consumed
+            d_next = __ldg(j.seg_desc + seg);
+            xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
         }
-        const int n = min(rem, kBatch);
+        int rem = d.y;
+        while (rem > 0) {
+            const int n = min(rem, kChunkRows - rpos);
+            const float* ws = ring + stage * kChunkFloats + rpos * kRowFloats + lane;
+            int t = 0;
+            for (; t + 4 <= n; t += 4) {
+                float wv[4][G];
+                F3 c[4];
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k)
-            if (k < n) c[k] = load_texel<SS>(j.src, s0 + k);
-        s0 += n;
-        rem -= n;
-        return n;
-    };
-
-    int r = 0;   // flat weight row of the patch = position in the ring modulo kRingRows
-    F3 cb[kBatch], cn[kBatch];
-    int nb = next_batch(cb);
-    while (nb > 0) {
-        const int nn = next_batch(cn);   // the following batch's loads are issued before this one is consumed
+                for (int k = 0; k < 4; ++k) {
+                    c[k] = load_texel<SS>(j.src, s0 + t + k);
 #pragma unroll
-        for (int k = 0; k < kBatch; ++k) {
-            if (k < nb) {
-                const int q = r / kChunkRows;            // chunk of this row
-                const int stage = q % kStages;
-                if (r % kChunkRows == 0)                  // first row of a chunk: its copy must have landed
-                    while (!mbar_try_wait(bars_s + stage * 8, (uint32_t)(q / kStages) & 1u)) {}
-                const float* ws = ring + (r % kRingRows) * kRowFloats + lane;
+                    for (int g = 0; g < G; ++g) wv[k][g] = ws[(t + k) * kRowFloats + g * 32];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        acc[g][0] = fmaf(wv[k][g], c[k].x, acc[g][0]);
+                        acc[g][1] = fmaf(wv[k][g], c[k].y, acc[g][1]);
+                        acc[g][2] = fmaf(wv[k][g], c[k].z, acc[g][2]);
+                    }
+            }
+            for (; t < n; ++t) {
+                const F3 c = load_texel<SS>(j.src, s0 + t);
 #pragma unroll
                 for (int g = 0; g < G; ++g) {
-                    const float wv = ws[g * 32];
-                    acc[g][0] = fmaf(wv, cb[k].x, acc[g][0]);
-                    acc[g][1] = fmaf(wv, cb[k].y, acc[g][1]);
-                    acc[g][2] = fmaf(wv, cb[k].z, acc[g][2]);
-                }
-                ++r;
-                if (r % kChunkRows == 0) {   // chunk consumed: hand its stage back to the copy engine
-                    __syncwarp();
-                    const int refill = q + kStages;
-                    if (lane == 0 && refill < nchunks) {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        const uint32_t bytes = (uint32_t)min(kChunkRows, total_rows - refill * kChunkRows) * kRowFloats * 4u;
-                        mbar_expect_tx(bars_s + stage * 8, bytes);
-                        bulk_g2s(ring_s + stage * kChunkFloats * 4, wsrc + (size_t)refill * kChunkFloats, bytes,
-                                 bars_s + stage * 8, pol);
-                    }
+                    const float wv = ws[t * kRowFloats + g * 32];
+                    acc[g][0] = fmaf(wv, c.x, acc[g][0]);
+                    acc[g][1] = fmaf(wv, c.y, acc[g][1]);
+                    acc[g][2] = fmaf(wv, c.z, acc[g][2]);
                 }
             }
+            s0 += n;
+            rem -= n;
+            rpos += n;
+            if (rpos == kChunkRows) {   // chunk consumed: hand its stage back to the copy engine, move on
+                __syncwarp();
+                const int refill = chunk + kStages;
+                if (lane == 0 && refill < nchunks) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    const uint32_t bytes = (uint32_t)min(kChunkRows, total_rows - refill * kChunkRows) * kRowFloats * 4u;
+                    mbar_expect_tx(bars_s + stage * 8, bytes);
+                    bulk_g2s(ring_s + stage * kChunkFloats * 4, wsrc + (size_t)refill * kChunkFloats, bytes,
+                             bars_s + stage * 8, pol);
+                }
+                ++chunk;
+                rpos = 0;
+                if (++stage == kStages) {
+                    stage = 0;
+                    parity ^= 1u;
+                }
+                if (chunk < nchunks)
+                    while (!mbar_try_wait(bars_s + stage * 8, parity)) {}
+            }
         }
-#pragma unroll
-        for (int k = 0; k < kBatch; ++k) cb[k] = cn[k];
-        nb = nn;
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) {
         const int o = patch_texel<G>(patch, lane, g, j.N, j.pwl);
         if (o >= j.texels) continue;
-        float rr = acc[g][0], gg = acc[g][1], b = acc[g][2];
+        float r = acc[g][0], gg = acc[g][1], b = acc[g][2];
         if (j.nan_where_zero != nullptr && __ldg(j.nan_where_zero + o) == 0.0f) {
             // the reference divides by the weight sum: an empty cone yields 0/0 (c_src/cubemap.cu:296-299 + ops.py:458)
-            rr = gg = b = __int_as_float(0x7fc00000);
+            r = gg = b = __int_as_float(0x7fc00000);
         }
         float* q = j.dst + (size_t)o * j.dst_stride;
-        q[0] = rr;
+        q[0] = r;
         q[1] = gg;
         q[2] = b;
     }
 }
 
-__global__ void __launch_bounds__(kGatherWarps * 32, 4) prefilter_gather_kernel(const __grid_constant__ GatherParams p) {
+__global__ void __launch_bounds__(kGatherWarps * 32) prefilter_gather_kernel(const __grid_constant__ GatherParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int wib = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

@@ -160,10 +160,13 @@ def choose_shape(res, roughness, ct, tab, bounds, device):
     cands = [sh for sh in SHAPES if lib.mrgs_prefilter_patch_count(res, sh[1], sh[0]) >= 0]
     if any(sh[1] == 2 for sh in cands):
         cands = [sh for sh in cands if sh[1] == 2]
+    # ... and weigh the padded slots with the per-byte cost measured for each width on the 6x512^2 chain (all levels in
+    # one shape: 8 lanes wide streams at 5.8 TB/s, 16 at 5.25, 32 at 4.9; profiles/r02_prefilter.md)
+    width_cost = {8: 1.0, 16: 1.11, 32: 1.19}
     best, best_score = (32, 1), None
     for shape in cands:
         _, _, (_, rows, _) = _count(_lib.PREFILTER_SPECULAR, res, shape, roughness, ct, tab, bounds, None, False, device)
-        score = rows * shape[1]
+        score = rows * shape[1] * width_cost[shape[0]]
         if best_score is None or score < best_score:
             best, best_score = shape, score
     return best, False

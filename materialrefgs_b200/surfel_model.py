@@ -356,7 +356,13 @@ class SurfelStore:
         sel = torch.logical_and(sel, torch.max(self.get_scaling, dim=1).values > self.percent_dense * scene_extent)
         stds = self.get_scaling[sel].repeat(N, 1)
         stds = torch.cat([stds, 0 * torch.ones_like(stds[:, :1])], dim=-1)
-        samples = torch.normal(mean=torch.zeros_like(stds), std=stds, generator=generator)
+        if generator is not None and generator.device != stds.device:
+            # a host generator with device-resident parameters: the draw happens where the generator lives, so every rank
+            # (and a CPU run of the same step) sees the same offsets whatever device holds its surfels
+            samples = torch.normal(mean=torch.zeros(stds.shape, device=generator.device), std=stds.to(generator.device),
+                                   generator=generator).to(stds.device)
+        else:
+            samples = torch.normal(mean=torch.zeros_like(stds), std=stds, generator=generator)
         rots = build_rotation(self.params["rotation"].detach()[sel]).repeat(N, 1, 1)
         new = {n: self.params[n].detach()[sel].repeat(N, *([1] * len(FIELDS[n].shape))) for n in FIELDS}
         new["xyz"] = torch.bmm(rots, samples.unsqueeze(-1)).squeeze(-1) + self.params["xyz"].detach()[sel].repeat(N, 1)

@@ -58,6 +58,18 @@ def _rel_err(a, b):
     return ((a - b).abs().max() / denom).item()
 
 
+def _assert_grads(ours: dict, ref_runs: list, what=""):
+    """north_star bar: 1e-3 relative to the tensor's max-norm against the reference. The reference's own float atomics
+    are order-dependent, so the comparison is against the MEDIAN of three reference runs and the bar is
+    max(1e-3, 2 x the reference's own run-to-run spread around that median) - never a blanket multiple of 1e-3."""
+    assert len(ref_runs) == 3
+    for k in ours:
+        ref_g = torch.stack([r[k] for r in ref_runs]).median(0).values
+        spread = max(_rel_err(r[k], ref_g) for r in ref_runs)
+        err = _rel_err(ours[k], ref_g)
+        assert err <= max(GRAD_RTOL, 2 * spread), (what, k, err, spread)
+
+
 def _scene(P, S, W, H, opacity="trained", view=1, scale_mult=1.0):
     dev = torch.device("cuda:0")
     cloud = synthetic.make_cloud(P, S=S, opacity=opacity, scale_mult=scale_mult).to(dev)
@@ -140,6 +152,7 @@ def test_forward_buffers_bit_exact(ref_ext, P, S, W, H, opacity):
     (100_000, 8, 800, 800, "trained", True),
     (100_000, 0, 800, 800, "init", True),
     (40_000, 18, 320, 240, "trained", False),   # render_volume-sized feature vector, precomputed colours
+    (1_000_000, 8, 800, 800, "trained", True),  # BASELINE config C3 itself: every gradient tensor at the headline size
 ])
 def test_forward_backward_vs_reference(ref_ext, P, S, W, H, opacity, use_sh):
     import materialrefgs_b200.diff_surfel_rasterization as ours
@@ -154,11 +167,7 @@ def test_forward_backward_vs_reference(ref_ext, P, S, W, H, opacity, use_sh):
     for k in ("color", "feature", "allmap"):
         if a[k].numel():
             assert (a[k] - b[k]).abs().max().item() <= IMG_ATOL, k
-    for k in a["grads"]:
-        ref_g = torch.stack([r["grads"][k] for r in refs]).median(0).values
-        spread = max(_rel_err(r["grads"][k], ref_g) for r in refs)
-        err = _rel_err(a["grads"][k], ref_g)
-        assert err <= max(GRAD_RTOL, 2 * spread), (k, err, spread)
+    _assert_grads(a["grads"], [r["grads"] for r in refs])
 
 
 def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
@@ -191,9 +200,7 @@ def test_c4_scale_unbounded_scene_vs_reference(ref_ext):
         assert (a_ - b_).abs().max().item() <= IMG_ATOL
     del geom_r, bin_r, img_r, geom, binning, img, br, bm
     a = _run(ours, cloud, cam, bg, grads)
-    b = _run(ref_ext, cloud, cam, bg, grads)
-    for k in a["grads"]:
-        assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
+    _assert_grads(a["grads"], [_run(ref_ext, cloud, cam, bg, grads)["grads"] for _ in range(3)], "C4")
 
 
 def test_debug_mode_matches_and_writes_snapshots(tmp_path, monkeypatch):
@@ -333,12 +340,15 @@ def test_c5_scale_view_batch_step_vs_reference(ref_ext):
 
     out = parallel.train_step_view_sharded(render_view, len(cams), arena)
     assert arena.bound(leaves)
-    refs = [_run(ref_ext, cloud, c, bg, grads) for c in cams]
-    for k in names:
-        want = sum(r["grads"][k] for r in refs).reshape(P, -1)
-        assert _rel_err(out[k], want) <= 2 * GRAD_RTOL, k
-    norm = sum(torch.linalg.norm(r["grads"]["means2D"][:, :2], dim=-1) * (r["radii"] > 0) for r in refs)
-    assert _rel_err(arena.stats[:, 0], norm) <= 2 * GRAD_RTOL
+    # three reference runs of the whole batch (its atomics are order-dependent): median + spread bar
+    batches = [[_run(ref_ext, cloud, c, bg, grads) for c in cams] for _ in range(3)]
+    refs = batches[0]
+    want = [{k: sum(r["grads"][k] for r in b).reshape(P, -1) for k in names} for b in batches]
+    for w, b in zip(want, batches):
+        w["stats0"] = sum(torch.linalg.norm(r["grads"]["means2D"][:, :2], dim=-1) * (r["radii"] > 0) for r in b)
+    mine = {k: out[k] for k in names}
+    mine["stats0"] = arena.stats[:, 0]
+    _assert_grads(mine, want, "C5")
     assert torch.equal(arena.stats[:, 1], sum((r["radii"] > 0).float() for r in refs))
     assert torch.equal(arena.max_radii, torch.maximum(refs[0]["radii"], refs[1]["radii"]).clamp_min(0))
 
@@ -363,12 +373,11 @@ def test_lower_sh_degrees(ref_ext, deg):
     cloud, cam, grads = _scene(20_000, 8, 256, 192)
     bg = torch.zeros(3, device=dev)
     a = _run(ours, cloud, cam, bg, grads, sh_degree=deg)
-    b = _run(ref_ext, cloud, cam, bg, grads, sh_degree=deg)
-    assert (a["color"] - b["color"]).abs().max().item() <= IMG_ATOL
+    refs = [_run(ref_ext, cloud, cam, bg, grads, sh_degree=deg) for _ in range(3)]
+    assert (a["color"] - refs[0]["color"]).abs().max().item() <= IMG_ATOL
     n = (deg + 1) ** 2
     assert not a["grads"]["shs"][:, n:].any()
-    for k in a["grads"]:
-        assert _rel_err(a["grads"][k], b["grads"][k]) <= 2 * GRAD_RTOL, k
+    _assert_grads(a["grads"], [r["grads"] for r in refs], f"sh degree {deg}")
 
 
 def test_precomputed_transmat_path(ref_ext):
@@ -387,7 +396,7 @@ def test_precomputed_transmat_path(ref_ext):
     T = refimpl.decode_mrgs_geom(out[6], P, S)["transMat"].clone()
     T[out[5] <= 0] = 0.0     # culled rows are uninitialised scratch
     res = {}
-    for name, mod in (("ours", ours), ("ref", ref_ext)):
+    for name, mod in (("ours", ours), ("ref", ref_ext), ("ref2", ref_ext), ("ref3", ref_ext)):
         Tl = T.clone().requires_grad_(True)
         m3 = cloud.means3D.clone().requires_grad_(True)
         op = cloud.opacities.clone().requires_grad_(True)
@@ -404,8 +413,8 @@ def test_precomputed_transmat_path(ref_ext):
     assert torch.equal(a["radii"], b["radii"])
     assert (a["color"] - b["color"]).abs().max().item() <= IMG_ATOL
     assert (a["allmap"] - b["allmap"]).abs().max().item() <= IMG_ATOL
-    for k in ("gT", "gm3", "gop", "gsh"):
-        assert _rel_err(a[k], b[k]) <= 2 * GRAD_RTOL, k
+    keys = ("gT", "gm3", "gop", "gsh")
+    _assert_grads({k: a[k] for k in keys}, [{k: res[n][k] for k in keys} for n in ("ref", "ref2", "ref3")], "transMat")
 
 
 def test_scale_modifier_and_small_fov(ref_ext):
@@ -415,11 +424,11 @@ def test_scale_modifier_and_small_fov(ref_ext):
     cloud, cam, grads = _scene(30_000, 8, 400, 400)
     bg = torch.zeros(3, device=dev)
     a = _run(ours, cloud, cam, bg, grads, scale_modifier=0.6)
-    b = _run(ref_ext, cloud, cam, bg, grads, scale_modifier=0.6)
+    refs = [_run(ref_ext, cloud, cam, bg, grads, scale_modifier=0.6) for _ in range(3)]
+    b = refs[0]
     assert torch.equal(a["radii"], b["radii"])
     assert (a["color"] - b["color"]).abs().max().item() <= IMG_ATOL
-    for k in a["grads"]:
-        assert _rel_err(a["grads"][k], b["grads"][k]) <= 5 * GRAD_RTOL, k
+    _assert_grads(a["grads"], [r["grads"] for r in refs], "scale_modifier")
 
 
 def test_mark_visible_and_api_errors(ref_ext):

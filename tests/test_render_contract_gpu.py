@@ -17,6 +17,31 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
+_MEASURED = []
+
+
+def _close_grads(ga, gb, name):
+    """End-to-end gradient check of a whole render() call. The shaded image is only piecewise differentiable, so the
+    bar is the relative L1 error plus a bound on the fraction of elements that are off by more than 1 % of the max-norm
+    (see the comment in test_render_surfel_contract); the measured values are logged to gpurun_out/ for the record."""
+    l1 = ((ga - gb).abs().sum() / gb.abs().sum().clamp_min(1e-20)).item()
+    out_frac = ((ga - gb).abs() > 1e-2 * gb.abs().max()).float().mean().item()
+    mx = ((ga - gb).abs().max() / gb.abs().max().clamp_min(1e-20)).item()
+    _MEASURED.append({"name": name, "rel_l1": l1, "outlier_fraction": out_frac, "rel_max": mx})
+    try:
+        import json
+        import os
+        os.makedirs("gpurun_out", exist_ok=True)
+        with open("gpurun_out/render_contract_errors.json", "w") as fh:
+            json.dump(_MEASURED, fh, indent=1)
+    except OSError:
+        pass
+    assert l1 <= L1_BAR and out_frac <= 1e-3, (name, l1, out_frac, mx)
+
+
+L1_BAR = 3e-3   # measured (gpurun_out/render_contract_errors.json): <= 2.5e-3 on the FakeModel case, <= 2e-4 elsewhere
+
+
 class FakeModel:
     """The getters render_surfel uses from scene/gaussian_model.py, over a synthetic cloud."""
     active_sh_degree = 3
@@ -110,10 +135,7 @@ def test_render_surfel_contract(ref_ext):
     # the two analytic values). Such a pixel can dominate the max-norm of ONE surfel's gradient, so this end-to-end
     # check uses the relative L1 error plus a bound on the fraction of outliers; the per-kernel tests keep the
     # max-norm bars (1e-3 rasterizer with identical upstream gradients, 1e-3 shading on a smooth G-buffer).
-    def close(a, b, name):
-        l1 = ((a - b).abs().sum() / b.abs().sum().clamp_min(1e-20)).item()
-        out_frac = ((a - b).abs() > 1e-2 * b.abs().max()).float().mean().item()
-        assert l1 <= 5e-3 and out_frac <= 1e-3, (name, l1, out_frac)
+    close = _close_grads
     for k in g_ours:
         close(g_ours[k], pc2.leaves[k].grad, k)
     close(g_ind, pc2.ind.grad, "indirect")
@@ -188,17 +210,10 @@ def test_render_surfel_contract_raw_parameters(ref_ext):
     for k in ("render", "specular_map", "diffuse_map", "rend_normal", "rend_alpha", "surf_depth", "roughness_map"):
         assert (out[k] - ref[k]).abs().max().item() <= 1e-4, k
     for k in pc.raw:
-        a, b = pc.raw[k].grad, pc2.raw[k].grad
-        l1 = ((a - b).abs().sum() / b.abs().sum().clamp_min(1e-20)).item()
-        out_frac = ((a - b).abs() > 1e-2 * b.abs().max()).float().mean().item()
-        assert l1 <= 5e-3 and out_frac <= 1e-3, (k, l1, out_frac)
+        _close_grads(pc.raw[k].grad, pc2.raw[k].grad, k)
 
 
 # ---- render_initial / render_volume (gaussian_renderer/__init__.py:94-222, :521-745) -----------------------------
-def _close_grads(ga, gb, name):
-    l1 = ((ga - gb).abs().sum() / gb.abs().sum().clamp_min(1e-20)).item()
-    out_frac = ((ga - gb).abs() > 1e-2 * gb.abs().max()).float().mean().item()
-    assert l1 <= 5e-3 and out_frac <= 1e-3, (name, l1, out_frac)
 
 
 def test_render_initial_contract(ref_ext):
