@@ -143,18 +143,6 @@ def measured_peak_hbm():
     return 6650.0, "fallback"
 
 
-def balanced_assignment(costs, world, per_rank):
-    """Longest-processing-time-first assignment of len(costs) = world * per_rank items to ranks with exactly
-    per_rank items each; returns a list of item-index lists. Deterministic, identical on every rank."""
-    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
-    load, out = [0.0] * world, [[] for _ in range(world)]
-    for i in order:
-        r = min((r for r in range(world) if len(out[r]) < per_rank), key=lambda r: (load[r], r))
-        out[r].append(i)
-        load[r] += costs[i]
-    return out
-
-
 # ------------------------------------------------------------------------------------------------
 class StepBase:
     """Scene, view schedule and the end-to-end plumbing (pinned host buffers, one copy stream, double-buffered device
@@ -185,7 +173,7 @@ class StepBase:
         if wl["batch_views"] is None:
             self.V = wl["views_per_rank"]
         else:
-            self.V = len(range(rank, wl["batch_views"], world))
+            self.V = wl["batch_views"] // world + (1 if rank < wl["batch_views"] % world else 0)
         self.total_views = wl["views_per_rank"] * world if wl["batch_views"] is None else wl["batch_views"]
         self.cost = [1.0] * N_CAMS       # per-camera cost (instances R of the last render), identical on all ranks
         self.last = {}
@@ -201,16 +189,15 @@ class StepBase:
         cams = [(i * T + k + i) % N_CAMS for k in range(T)]        # + i: every rank cycles through all cameras
         if W == 1:
             return cams
-        if T % W == 0:
-            parts = balanced_assignment([self.cost[c] for c in cams], W, T // W)
-            return [cams[k] for k in parts[self.rank]]
-        return cams[self.rank::W]
+        from materialrefgs_b200.parallel import assign_views_balanced   # (multi-rank = our arm only)
+        parts = assign_views_balanced([self.cost[c] for c in cams], W)
+        return [cams[k] for k in parts[self.rank]]
 
     # ---- end-to-end plumbing ------------------------------------------------------------------------------
     def _e2e_init(self):
         if hasattr(self, "copy_stream"):
             return
-        V = max(self.V, 1)
+        V = self.ring = max(min(self.V, 8), 1)   # result buffers per step parity (a ring when a step has more views)
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.in_slots = [None, None]
         self.in_events = [torch.cuda.Event(), torch.cuda.Event()]
@@ -219,7 +206,7 @@ class StepBase:
         # two sets of pinned result buffers (step parity): one is read by the host while the other is being filled
         self.img_host = [[torch.empty((3, self.wl["H"], self.wl["W"]), dtype=torch.float32).pin_memory()
                           for _ in range(V)] for _ in range(2)]
-        self.loss_host = [torch.empty(V, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self.loss_host = [torch.zeros(V, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.result_events = [torch.cuda.Event(), torch.cuda.Event()]
         self.result_pending = [False, False]
 
@@ -250,9 +237,15 @@ class StepBase:
         img = self.last["render"].detach()
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(done)
-            self.img_host[par][v].copy_(img, non_blocking=True)
+            self.img_host[par][v % self.ring].copy_(img, non_blocking=True)
             if loss is not None:
-                self.loss_host[par][v:v + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                self.loss_host[par][v % self.ring:v % self.ring + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            if getattr(self, "graphs", None) is not None:   # replayed views rewrite the same output tensors
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                if not hasattr(self, "out_busy"):
+                    self.out_busy = {}
+                self.out_busy[self.last_view] = ev
         img.record_stream(self.copy_stream)
 
     def _e2e_consume(self, par):
@@ -261,7 +254,8 @@ class StepBase:
             return 0.0
         self.result_events[par].synchronize()
         self.result_pending[par] = False
-        return float(sum(float(self.loss_host[par][v]) + float(self.img_host[par][v][0, 0, 0]) for v in range(self.V)))
+        return float(sum(float(self.loss_host[par][v]) + float(self.img_host[par][v][0, 0, 0])
+                         for v in range(min(self.V, self.ring))))
 
     def e2e_finish(self):
         return self._e2e_consume(0) + self._e2e_consume(1)
@@ -301,6 +295,7 @@ class StepBase:
             else:
                 c = self.cam_dev[view]
                 cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
+            self.last_view = view
             loss = self.render(view, cam_mats, up, last=(v == len(views) - 1))
             if e2e:  # device -> host: the rendered image and the loss of every view (copy stream, pinned target)
                 self._e2e_readback(i & 1, v, loss)
@@ -338,8 +333,16 @@ class OursStep(StepBase):
         # ONE flat buffer: [parameter gradients | densification statistics | cubemap texel-gradient sink]; the segments
         # are the parameters' .grad AND the rasterizer's grad_sink, the tail is EnvLight's level-gradient sink: every
         # producer kernel writes straight into the buffer that is all-reduced (materialrefgs_b200/parallel.py)
-        self.arena = GradArena.create(wl["P"], dev, extra_floats=4 * texels if self.train else 0)
+        self.arena = GradArena.create(wl["P"], dev, extra_floats=4 * texels) if self.train else None
         self.sink = None
+        self.graphs, self.graph_launches, self.replayed_launches = None, {}, 0
+        if self.train and wl.get("graphs", True):
+            # one CUDA graph per camera: the whole view (rasterize, shade, loss, backward, statistics) replays as one
+            # launch; the environment chain keeps its addresses (static_chain), per-view inputs live in fixed slots
+            from materialrefgs_b200.graphs import ViewGraphs
+            self.graphs = ViewGraphs(dev)
+            if self.env is not None:
+                self.env.static_chain = True
         if self.train:
             self.arena.bind(self.leaves)
             self.sink = self.arena.views
@@ -356,6 +359,29 @@ class OursStep(StepBase):
             self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
 
     def render(self, view, cam_mats, up, last=False):
+        c = self.cam_dev[view]
+        slots = (c.world_view_transform, c.full_proj_transform, c.camera_center)
+        if self.graphs is None:
+            return self._view(view, cam_mats, up, last)
+        if cam_mats[0] is not slots[0]:      # end-to-end mode: freshly copied inputs go into the graph's fixed slots
+            for dst, src in zip(slots, cam_mats):
+                dst.copy_(src, non_blocking=True)
+            for k, v in up.items():
+                self.up[k].copy_(v, non_blocking=True)
+        busy = getattr(self, "out_busy", {}).pop(view, None)
+        if busy is not None:                 # the graph's output tensors are still being copied to the host
+            torch.cuda.current_stream(self.dev).wait_event(busy)
+        first = view not in self.graphs.graphs
+        n0 = int(self.lib.mrgs_launch_count())
+        loss, image, radii = self.graphs.run(view, lambda: self._view(view, slots, self.up, False, True))
+        if first:      # launches recorded while capturing = launches every replay performs
+            self.graph_launches[view] = (int(self.lib.mrgs_launch_count()) - n0) // 2
+        else:
+            self.replayed_launches += self.graph_launches[view]
+        self.last = {"radii": radii, "render": image, "loss": loss}
+        return loss
+
+    def _view(self, view, cam_mats, up, last=False, as_tuple=False):
         cam = self.cams[view]
         wvt, proj, center = cam_mats
         wl = self.wl
@@ -367,7 +393,8 @@ class OursStep(StepBase):
             contrib, color, feat, radii, allmap = rast(
                 means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
                 features=L["features"], scales=L["scales"], rotations=L["rotations"])
-            self.cost[view] = float(rast.num_rendered) if getattr(rast, "num_rendered", None) else self.cost[view]
+            if not torch.cuda.is_current_stream_capturing() and getattr(rast, "num_rendered", None):
+                self.cost[view] = float(rast.num_rendered)
             if self.env is not None:
                 out = self.shade(self.env, color, feat, allmap, cam.HWK, cam.R, self.bg)
                 image, normal = out["render"], out["rend_normal"]
@@ -376,16 +403,48 @@ class OursStep(StepBase):
             loss = None
             if self.train:
                 self.means2D.grad = None   # the densification norm is taken per view (gaussian_model.py:1059-1061)
-                loss = (image * up["render"]).sum() + (allmap * up["allmap"]).sum()
+                # the loss of a real step is outside the path: its gradient maps arrive as inputs and enter the backward
+                # directly; the scalar read back per view is the photometric term of it
+                loss = (image.detach() * up["render"]).sum()
+                outs, gs = [image, allmap], [up["render"], up["allmap"]]
                 if normal is not None:
-                    loss = loss + (normal * up["normal"]).sum()
+                    outs.append(normal)
+                    gs.append(up["normal"])
                 if last and self.world > 1 and self.env is not None:
                     self.env.after_sink_backward = self._sink_ready   # fires right after the last shading backward
-                loss.backward()
+                torch.autograd.backward(outs, gs)
                 if self.world > 1:
                     self.arena.accumulate_view({}, self.means2D.grad, radii)
+        if as_tuple:
+            return loss, image, radii
         self.last = {"radii": radii, "render": image, "loss": loss}
         return loss
+
+    def measure_costs(self):
+        """Instance count R of every camera from one forward-only rasterization (untimed set-up)."""
+        L = self.leaves
+        with torch.no_grad():
+            for v, c in enumerate(self.cam_dev):
+                cam = self.cams[v]
+                rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0,
+                              c.world_view_transform, c.full_proj_transform, self.wl["sh_degree"], c.camera_center, False, False)
+                rast = self.GR(rs)
+                rast(means3D=L["means3D"], means2D=None, opacities=L["opacities"], shs=L["shs"], features=L["features"],
+                     scales=L["scales"], rotations=L["rotations"])
+                self.cost[v] = float(rast.num_rendered or 1.0)
+        torch.cuda.synchronize()
+
+    def prime_graphs(self):
+        """Capture every camera's view graph before anything is timed (one eager view + one capture per camera)."""
+        if self.graphs is None:
+            return
+        self.begin_step()
+        for v in range(N_CAMS):
+            c = self.cam_dev[v]
+            self.render(v, (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up)
+        self.end_step()
+        torch.cuda.synchronize()
+        self.graphs.check()
 
     def _sink_ready(self):
         """The cubemap texel gradients of this rank are complete once the LAST view's shading backward is enqueued: their
@@ -399,11 +458,12 @@ class OursStep(StepBase):
         if self.world > 1:
             # arena allreduce (272 MB at 1 M surfels) on NCCL's stream WHILE the main stream runs the build_mips backward,
             # which only needs the texel-gradient sink (reduced above, under the last view's rasterizer backward)
+            if self.env is not None and getattr(self, "sink_work", None) is None:
+                self.sink_work = self.arena.allreduce_extra_async()   # (graph replay: no hook inside the last view)
             work = self.arena.allreduce_main_async()
             if self.env is not None:
-                if getattr(self, "sink_work", None) is not None:
-                    self.sink_work.wait()
-                    self.sink_work = None
+                self.arena.wait(self.sink_work)
+                self.sink_work = None
                 self.env.flush_level_grads()
             self.arena.wait(work)
         elif self.env is not None:
@@ -493,9 +553,9 @@ class ReferenceStep(StepBase):
                 means3D=L["means3D"], means2D=self.means2D, opacities=L["opacities"], shs=L["shs"],
                 features=L["features"], scales=L["scales"], rotations=L["rotations"])
             loss = None
-            if self.train:
-                loss = (color * up["render"]).sum() + (allmap * up["allmap"]).sum() + (feat * up["feature"]).sum()
-                loss.backward()
+            if self.train:   # same glue as our arm: upstream gradient maps enter the backward directly
+                loss = (color.detach() * up["render"]).sum()
+                torch.autograd.backward([color, allmap, feat], [up["render"], up["allmap"], up["feature"]])
         self.last = {"radii": radii, "render": color, "loss": loss}
         return loss
 
@@ -580,12 +640,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the surfel count (debug only)")
     ap.add_argument("--views-per-rank", type=int, default=None)
+    ap.add_argument("--graphs", type=int, default=1, help="0: launch every view eagerly instead of replaying CUDA graphs")
     a = ap.parse_args()
     wl = dict(WORKLOADS[a.config])
     if a.views_per_rank:
         wl["views_per_rank"] = max(1, a.views_per_rank)
     if a.P:
         wl["P"] = a.P
+    wl["graphs"] = bool(a.graphs)
     a.warmup = max(a.warmup, 3)
 
     if not torch.cuda.is_available():
@@ -621,23 +683,24 @@ def main():
 
     # every rank learns every camera's cost once (forward only, untimed): the view schedule is then identical everywhere
     if ours and world > 1:
-        with torch.no_grad():
-            for v in range(N_CAMS):
-                c = stepper.cam_dev[v]
-                stepper.render(v, (c.world_view_transform, c.full_proj_transform, c.camera_center), stepper.up)
-        torch.cuda.synchronize()
+        stepper.measure_costs()
 
     # ---- device-resident timing -------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()           # started before the warm-up so its own start-up cost is not timed
+    graphs = ours and getattr(stepper, "graphs", None) is not None
+    if ours:
+        # per-stage CUDA events: enabled before the view graphs are captured, so that the graphs carry them as
+        # external-event nodes and every replay inside the timed region re-records them
+        stepper.lib.mrgs_profile_enable(1)
+        stepper.prime_graphs()
     for i in range(a.warmup):
         stepper.step(i)
     barrier(world)
     if ours:
-        stepper.lib.mrgs_profile_enable(1)
         stepper.lib.mrgs_profile_reset()
-        launches0 = int(stepper.lib.mrgs_launch_count())
+        launches0 = int(stepper.lib.mrgs_launch_count()) + stepper.replayed_launches
     if rank == 0:
         sampler.mark()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -645,14 +708,19 @@ def main():
     e0.record()
     for i in range(a.steps):
         stepper.step(a.warmup + i)
+        if graphs and i % 4 == 3:
+            stepper.lib.mrgs_profile_collect_captured()   # one sample per captured stage (waits for this step's last view)
     e1.record()
     barrier(world)
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     if ours:
         prof = stepper._lib.profile_read()
-        launches = int(stepper.lib.mrgs_launch_count()) - launches0
+        launches = int(stepper.lib.mrgs_launch_count()) + stepper.replayed_launches - launches0
         stepper.lib.mrgs_profile_enable(0)
+        if graphs:
+            torch.cuda.synchronize()
+            stepper.graphs.check()
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms], device=dev)
@@ -701,6 +769,7 @@ def main():
         "config": {"workload": wl["text"], "name": a.config,
                    "P": P, "Pv": Pv, "N": N, "S": wl["S"], "views_per_step": views_per_step,
                    "views_per_rank": stepper.V, "parallelism": par,
+                   "cuda_graphs": bool(ours and getattr(stepper, "graphs", None) is not None),
                    "l2": "no explicit flush: per-step working set (~0.9 GB of surfel records, instance lists and gradient "
                          "arenas + 2 x 5 GB of prefilter weights streamed once per step) exceeds the 126 MB L2"},
         "e2e": {"value": views_per_step * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,

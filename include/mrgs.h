@@ -39,7 +39,8 @@
  *
  * ABI history: 5 = gradient sink (accumulate) in mrgs_backward; 6 = mrgs_geometry_loss_*, mrgs_img_grad_weight,
  * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query;
- * 7 = prefilter plans (mrgs_prefilter_*), mrgs_mip_pyramid_forward, mrgs_mip_chain_backward.
+ * 7 = prefilter plans (mrgs_prefilter_*), mrgs_mip_pyramid_forward, mrgs_mip_chain_backward;
+ * 8 = MrgsForwardArgs.no_wait / count_out (capture-safe forward), mrgs_profile_collect_captured.
  */
 #ifndef MRGS_H_INCLUDED
 #define MRGS_H_INCLUDED
@@ -51,7 +52,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 7
+#define MRGS_ABI_VERSION 8
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -175,6 +176,13 @@ typedef struct MrgsForwardArgs {
     int32_t num_rendered;          /* R, also the reference's first return value        */
     void* binning_buffer;          /* binning_scratch, or what binning_alloc returned (NULL if R == 0) */
     int64_t binning_capacity_used; /* instance count binning_buffer is laid out for (mrgs_binning_layout) */
+    /* Capture-safe mode (CUDA-graph capture of a whole view): with no_wait != 0 the call needs the optimistic buffer
+     * above, enqueues everything, NEVER waits and never calls binning_alloc; num_rendered then returns
+     * binning_capacity (the layout key for the backward) and the real R is copied to *count_out (optional, PINNED host
+     * int32) by the stream - the caller checks R <= binning_capacity after the stream (or a replay of the graph) has
+     * run; if that fails the frame's results are invalid and must be redone with a larger capacity. */
+    int32_t no_wait;
+    int32_t* count_out;
 } MrgsForwardArgs;
 
 typedef struct MrgsBackwardArgs {
@@ -473,6 +481,11 @@ MRGS_API int mrgs_mip_pyramid_forward(const float* base, int32_t res, int32_t nu
 MRGS_API int mrgs_mip_chain_backward(int32_t res, int32_t num_levels, float* const* grads3, const float* extra_last3,
                                      void* stream);
 
+/* Stage timing under CUDA-graph replay: stage scopes that run while their stream is being captured record their
+ * events as external-event nodes, so every replay re-records them; this call waits for the captured stages' end
+ * events and adds one sample each (call it after a replay has been enqueued and before the next one is). */
+MRGS_API void mrgs_profile_collect_captured(void);
+
 MRGS_API int mrgs_forward(MrgsForwardArgs* args, void* stream);
 MRGS_API int mrgs_backward(const MrgsBackwardArgs* args, void* stream);
 MRGS_API int mrgs_mark_visible(int32_t P, const float* means3D, const float* viewmatrix,
@@ -562,7 +575,7 @@ MRGS_API int mrgs_img_grad_weight(const float* img, int32_t channels, int32_t he
 /* Densification statistics of one rendered view, one fused pass over the P surfels
  * (GaussianModel.add_densification_stats scene/gaussian_model.py:1059-1061 and the max_radii2D update
  * train_refnerf.py:1416-1418). For every surfel with radii > 0:
- *   stats[i][0] += |dL_dmeans2D[i].xy|      (xyz_gradient_accum)
+ *   stats[i][0] += |dL_dmeans2D[i]|         (xyz_gradient_accum; all three components like torch.norm(grad, dim=-1))
  *   stats[i][1] += 1                        (denom)
  *   max_radii[i] = max(max_radii[i], radii[i])
  * dL_dmeans2D is [P,3] (the screen-space gradient the backward returns), stats [P,2], max_radii int32 [P]. */

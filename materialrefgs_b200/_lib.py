@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 7
+MRGS_ABI_VERSION = 8
 MAX_FEATURES = 24
 TILE = 16
 
@@ -54,6 +54,7 @@ class ForwardArgs(C.Structure):
         ("binning_alloc", alloc_fn), ("binning_ctx", C.c_void_p),
         ("binning_scratch", _fp), ("binning_scratch_bytes", C.c_size_t), ("binning_capacity", C.c_int64),
         ("num_rendered", C.c_int32), ("binning_buffer", _fp), ("binning_capacity_used", C.c_int64),
+        ("no_wait", C.c_int32), ("count_out", _fp),
     ]
 
 
@@ -159,6 +160,7 @@ SYMBOLS = {
     "mrgs_profile_reset": (None, []),
     "mrgs_profile_read": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]),
     "mrgs_launch_count": (C.c_int64, []),
+    "mrgs_profile_collect_captured": (None, []),
     "mrgs_shade_forward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_shade_backward": (C.c_int, [C.POINTER(ShadeArgs), C.c_void_p]),
     "mrgs_envlight_query": (C.c_int, [C.POINTER(ShadeArgs), C.c_int64, _fp, _fp, _fp, C.c_void_p]),

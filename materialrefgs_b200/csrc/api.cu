@@ -55,6 +55,7 @@ struct Profiler {
     cudaEvent_t ev[MRGS_STAGE_COUNT][2];
     bool created = false;
     bool pending[MRGS_STAGE_COUNT] = {};
+    bool captured[MRGS_STAGE_COUNT] = {};   // recorded inside a stream capture: re-recorded by every graph replay
     double ms[MRGS_STAGE_COUNT] = {};
     long long calls[MRGS_STAGE_COUNT] = {};
     long long launches = 0;
@@ -89,6 +90,13 @@ struct StageScope {
             }
             g_prof.created = true;
         }
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        capturing = cudaStreamIsCapturing(stream, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusActive;
+        if (capturing) {   // an external-event node: every replay of the graph records it again
+            g_prof.pending[stage] = false;
+            cudaEventRecordWithFlags(g_prof.ev[stage][0], stream, cudaEventRecordExternal);
+            return;
+        }
         // one in-flight measurement per stage: only THIS stage's previous pair is waited for (it finished a
         // whole step ago), never the still-running tail of the previous step
         prof_collect_one(stage);
@@ -96,9 +104,15 @@ struct StageScope {
     }
     ~StageScope() {
         if (!g_prof.enabled) return;
+        if (capturing) {
+            cudaEventRecordWithFlags(g_prof.ev[stage][1], stream, cudaEventRecordExternal);
+            g_prof.captured[stage] = true;
+            return;
+        }
         cudaEventRecord(g_prof.ev[stage][1], stream);
         g_prof.pending[stage] = true;
     }
+    bool capturing = false;
 };
 
 }  // namespace mrgs
@@ -116,6 +130,17 @@ size_t mrgs_grad_arena_bytes(int32_t P, int32_t S) {
 }
 
 void mrgs_profile_enable(int32_t on) { g_prof.enabled = on != 0; }
+void mrgs_profile_collect_captured(void) {
+    for (int s = 0; s < MRGS_STAGE_COUNT; ++s) {
+        if (!g_prof.captured[s]) continue;
+        float t = 0.f;
+        if (cudaEventSynchronize(g_prof.ev[s][1]) == cudaSuccess &&
+            cudaEventElapsedTime(&t, g_prof.ev[s][0], g_prof.ev[s][1]) == cudaSuccess && t >= 0.f) {
+            g_prof.ms[s] += t;
+            g_prof.calls[s] += 1;
+        }
+    }
+}
 void mrgs_profile_reset(void) {
     prof_collect();
     for (int s = 0; s < MRGS_STAGE_COUNT; ++s) {
@@ -224,9 +249,11 @@ __global__ void densify_stats_kernel(int P, const float* __restrict__ g, const i
     if (i >= P) return;
     const int32_t r = radii[i];
     if (r <= 0) return;
-    const float gx = g[3 * i], gy = g[3 * i + 1];
+    // torch.norm(viewspace_point_tensor.grad[filter], dim=-1): all three components (gaussian_model.py:1060); the
+    // rasterizer leaves z at zero
+    const float gx = g[3 * i], gy = g[3 * i + 1], gz = g[3 * i + 2];
     float2 s = stats[i];
-    s.x += sqrtf(gx * gx + gy * gy);
+    s.x += sqrtf(gx * gx + gy * gy + gz * gz);
     s.y += 1.0f;
     stats[i] = s;
     max_radii[i] = max(max_radii[i], r);
@@ -481,8 +508,10 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
             return MRGS_ERR_CUDA;
         }
         const uint32_t* R_dev = offsets + a->P - 1;
-        MRGS_CUDA_OK(cudaMemcpyAsync(slot, R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
-        MRGS_CUDA_OK(cudaEventRecord(r_ready, stream));
+        if (!a->no_wait) {
+            MRGS_CUDA_OK(cudaMemcpyAsync(slot, R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            MRGS_CUDA_OK(cudaEventRecord(r_ready, stream));
+        }
 
         // instance expansion, tile sort, tile ranges and the blend for a binning buffer laid out for
         // `cap` instances; with dev_count the kernels take the real count from the device
@@ -545,6 +574,18 @@ int mrgs_forward(MrgsForwardArgs* a, void* stream_) {
             const int st = bin_and_render((char*)a->binning_scratch, cap, R_dev);
             if (st != MRGS_OK) return st;
             rendered = true;
+        }
+        if (a->no_wait) {   // capture-safe: nothing below may wait on the stream
+            if (!rendered) {
+                set_error("mrgs_forward: no_wait needs binning_scratch/binning_capacity (and the look-back sort)");
+                return MRGS_ERR_INVALID_ARGUMENT;
+            }
+            if (a->count_out != nullptr)
+                MRGS_CUDA_OK(cudaMemcpyAsync(a->count_out, R_dev, sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+            a->binning_buffer = a->binning_scratch;
+            a->binning_capacity_used = cap;
+            a->num_rendered = (int32_t)cap;
+            return MRGS_OK;
         }
         MRGS_CUDA_OK(cudaEventSynchronize(r_ready));
         R = *slot;

@@ -30,6 +30,22 @@ def shard_views(n_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, n_views, world))
 
 
+def assign_views_balanced(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Deal len(costs) views to `world` ranks by cost (e.g. the instance count R of each camera's last render, which the
+    forward returns to the host anyway): longest-processing-time-first with equal counts per rank (the remainder goes to
+    the lightest ranks), so that no rank waits for the slowest one at the step's collective. Deterministic: every
+    rank computes the same assignment from the same cost table. Returns the item indices of every rank."""
+    n = len(costs)
+    cap = [n // world + (1 if r < n % world else 0) for r in range(world)]
+    order = sorted(range(n), key=lambda i: (-costs[i], i))
+    load, out = [0.0] * world, [[] for _ in range(world)]
+    for i in order:
+        r = min((r for r in range(world) if len(out[r]) < cap[r]), key=lambda r: (load[r], r))
+        out[r].append(i)
+        load[r] += costs[i]
+    return out
+
+
 @dataclass
 class GradArena:
     """ONE flat fp32 buffer holding, back to back, a contiguous [P, w] segment per gradient field and
@@ -110,7 +126,7 @@ class GradArena:
                                               self.max_radii.data_ptr(), C.c_void_p(stream)), "mrgs_densify_stats")
             return
         vis = radii > 0
-        norm = torch.linalg.norm(viewspace_grad[:, :2], dim=-1)
+        norm = torch.linalg.norm(viewspace_grad, dim=-1)      # all components, like gaussian_model.py:1060
         self.stats[:, 0].add_(torch.where(vis, norm, torch.zeros_like(norm)))
         self.stats[:, 1].add_(vis.to(torch.float32))
         torch.maximum(self.max_radii, torch.where(vis, radii, torch.zeros_like(radii)), out=self.max_radii)

@@ -294,8 +294,12 @@ class MipChain:
     def level_views(self, flat, width):
         return [flat[self.offsets[l]:self.offsets[l + 1]].view(6, r, r, width) for l, r in enumerate(self.sizes)]
 
-    def forward(self, base: torch.Tensor):
-        """base [6,res,res,3] -> ([prefiltered level l: [6,res>>l,res>>l,3]], diffuse [6,rmin,rmin,3])."""
+    _static = None
+
+    def forward(self, base: torch.Tensor, static: bool = False):
+        """base [6,res,res,3] -> ([prefiltered level l: [6,res>>l,res>>l,3]], diffuse [6,rmin,rmin,3]).
+        static: write into the chain's own persistent output buffers (every call returns tensors over the SAME storage),
+        which is what consumers captured in a CUDA graph need."""
         lib = _lib.load()
         dev = self.device
         base = base.detach().contiguous()
@@ -303,8 +307,13 @@ class MipChain:
         with torch.cuda.device(dev):
             _lib.check(lib.mrgs_mip_pyramid_forward(base.data_ptr(), self.res, self.n, _ptr_array(raw), _stream(dev)),
                        "mrgs_mip_pyramid_forward")
-        levels = [torch.empty((6, r, r, 3), dtype=torch.float32, device=dev) for r in self.sizes]
-        diffuse = torch.empty((6, self.sizes[-1], self.sizes[-1], 3), dtype=torch.float32, device=dev)
+        if static and self._static is not None:
+            levels, diffuse = self._static
+        else:
+            levels = [torch.empty((6, r, r, 3), dtype=torch.float32, device=dev) for r in self.sizes]
+            diffuse = torch.empty((6, self.sizes[-1], self.sizes[-1], 3), dtype=torch.float32, device=dev)
+            if static:
+                self._static = (levels, diffuse)
         jobs = [(self.spec[l][0], raw[l], 4, levels[l], 3, self.spec[l][0].wsum) for l in range(self.n)]
         jobs.append((self.diff[0], raw[-1], 4, diffuse, 3, None))
         apply_jobs(jobs, False, dev)
@@ -361,25 +370,29 @@ class _BuildMips(torch.autograd.Function):
     """base -> (level 0, ..., level n-1, diffuse): EnvLight.build_mips (scene/light.py:72-86) as one autograd node."""
 
     @staticmethod
-    def forward(ctx, base, chain: MipChain):
-        levels, diffuse = chain.forward(base)
+    def forward(ctx, base, chain: MipChain, static: bool = False):
+        levels, diffuse = chain.forward(base, static)
         ctx.chain = chain
         ctx.set_materialize_grads(False)
+        if static:      # fresh tensor objects over the persistent storage (an autograd output must not be reused)
+            levels, diffuse = [t.view(t.shape) for t in levels], diffuse.view(diffuse.shape)
         return (*levels, diffuse)
 
     @staticmethod
     def backward(ctx, *grads):
         chain: MipChain = ctx.chain
         g_levels, g_diffuse = grads[:-1], grads[-1]
+        if g_diffuse is None and all(g is None for g in g_levels):
+            return None, None, None  # e.g. the texel gradients went to EnvLight's sink instead of through autograd
         grad4 = None
         if any(g is not None for g in g_levels):
             grad4 = torch.zeros((chain.texels, 4), dtype=torch.float32, device=chain.device)
             for l, g in enumerate(g_levels):
                 if g is not None:
                     grad4[chain.offsets[l]:chain.offsets[l + 1], :3] = g.reshape(-1, 3)
-        return chain.backward(grad4, g_diffuse), None
+        return chain.backward(grad4, g_diffuse), None, None
 
 
-def build_mips(base, chain: MipChain):
-    outs = _BuildMips.apply(base, chain)
+def build_mips(base, chain: MipChain, static: bool = False):
+    outs = _BuildMips.apply(base, chain, static)
     return list(outs[:-1]), outs[-1]

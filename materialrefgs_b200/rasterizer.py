@@ -132,6 +132,17 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
     # library can enqueue the whole forward before it waits for R (include/mrgs.h, MrgsForwardArgs)
     scratch = None
     cap = _capacity_hint.get(dev.index, 0) if _OPTIMISTIC else 0
+    capturing = torch.cuda.is_current_stream_capturing()
+    if capturing:
+        # CUDA-graph capture of a view (graphs.py): no host wait is possible, so the call runs in the library's no_wait
+        # mode against the capacity learnt from earlier frames; the real instance count lands in a pinned int the
+        # graph's owner checks after a replay (captured_counts_ok)
+        if cap <= 0:
+            raise RuntimeError("rasterizer: render at least one frame on this device before capturing a CUDA graph "
+                               "(the capture needs an instance-capacity estimate)")
+        count = torch.zeros(1, dtype=torch.int32).pin_memory()
+        _captured_counts.append((count, cap))
+        a.no_wait, a.count_out = 1, count.data_ptr()
     if cap > 0:
         scratch = torch.empty(lib.mrgs_binning_bytes(cap), dtype=torch.uint8, device=dev)
         a.binning_scratch, a.binning_scratch_bytes, a.binning_capacity = scratch.data_ptr(), scratch.numel(), cap
@@ -146,7 +157,7 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
         binning = scratch if (scratch is not None and a.binning_buffer == scratch.data_ptr()) else \
             torch.empty(0, dtype=torch.uint8, device=dev)
     binning.mrgs_capacity = int(a.binning_capacity_used)   # layout key for the debug decoders
-    if _OPTIMISTIC:
+    if _OPTIMISTIC and not capturing:
         want = (R + R // 4 + 65535) & ~65535
         if want > cap:
             _capacity_hint[dev.index] = want
@@ -154,6 +165,21 @@ def rasterize_forward_raw(bg, means3D, colors_precomp, features, opacities, scal
 
 
 _last_num_rendered: dict = {}
+_captured_counts: list = []      # (pinned int32 [1] written by every replay, capacity) per captured forward
+
+
+def captured_counts_ok() -> bool:
+    """After a synchronisation: did every captured forward's last replay fit its binning capacity? If not, that
+    frame's outputs are invalid: raise the capacity (render the view eagerly once) and capture again."""
+    return all(int(c[0]) <= cap for c, cap in _captured_counts)
+
+
+def reserve_capacity(device, instances: int) -> None:
+    """Make the optimistic / captured binning buffers of `device` hold at least `instances` (tile, surfel) pairs."""
+    dev = torch.device(device)
+    want = (int(instances) + 65535) & ~65535
+    if want > _capacity_hint.get(dev.index, 0):
+        _capacity_hint[dev.index] = want
 
 
 def rasterize_backward_raw(bg, means3D, radii, colors_precomp, features, scales, rotations,

@@ -214,8 +214,13 @@ def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, 
     camera exactly as the reference passes `viewpoint_camera.HWK / .R`."""
     cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb,
            getattr(envmap, "level_grad_sink", None), envmap)
+    levels = envmap.specular
+    if cfg[5] is not None:
+        # sink mode: the texel gradients go to the sink, not through autograd - the view's autograd graph need not (and,
+        # when the view is captured in a CUDA graph, must not) reach back into the graph build_mips() recorded earlier
+        levels = [l.detach() for l in levels]
     final, specular, direct, normal_w, diffuse = _ShadeSurfel.apply(
-        rendered_image, rendered_features, allmap, bg_color, cfg, *envmap.specular)
+        rendered_image, rendered_features, allmap, bg_color, cfg, *levels)
     return {
         "render": final,
         "refl_strength_map": rendered_features[:1],
@@ -387,6 +392,7 @@ class EnvLight(torch.nn.Module):
         self.build_mips()
 
     _chain = None
+    static_chain = False    # True: build_mips() rewrites the SAME level buffers every time (CUDA-graph consumers, graphs.py)
 
     def chain_roughnesses(self, n):
         """Roughness of every level as build_mips assigns them (scene/light.py:81-86)."""
@@ -414,7 +420,7 @@ class EnvLight(torch.nn.Module):
             except pf.PrefilterTooLarge:
                 self._chain = None
         if self._chain is not None:
-            self.specular, self.diffuse = pf.build_mips(self.base, self._chain)
+            self.specular, self.diffuse = pf.build_mips(self.base, self._chain, self.static_chain)
         else:
             self.specular = [self.base]
             while self.specular[-1].shape[1] > self.min_res:

@@ -31,7 +31,7 @@ def expected():
         v = fake_view(i)
         flat += torch.cat([v["grads"][n].reshape(P, -1) for n, _ in parallel.GRAD_FIELDS], 1)
         vis = v["radii"] > 0
-        stats[:, 0] += torch.linalg.norm(v["viewspace_grad"][:, :2], dim=-1) * vis
+        stats[:, 0] += torch.linalg.norm(v["viewspace_grad"], dim=-1) * vis
         stats[:, 1] += vis.float()
         mx = torch.maximum(mx, v["radii"])
     return flat, stats, mx
@@ -54,6 +54,25 @@ def _worker(rank, world, port, q):
             return fake_view(i)
         views = parallel.train_step_view_sharded(render, NV, arena)
         ev = parallel.eval_views_sharded(lambda i: torch.tensor(float(i)), 7)
+        # the same exchange in its two overlappable pieces, with a tail (the cubemap texel-gradient sink) in the SAME buffer
+        a2 = parallel.GradArena.create(P, "cpu", extra_floats=4 * 11)
+        assert a2.extra.numel() == 44 and a2.extra.data_ptr() == a2.flat.data_ptr() + 4 * (a2.flat.numel() - 44)
+        assert (a2.extra.data_ptr() - a2.flat.data_ptr()) % 16 == 0 and a2.main.numel() == P * 68
+        for i in parallel.shard_views(NV, rank, world):
+            v = fake_view(i)
+            a2.accumulate_view(v["grads"], v["viewspace_grad"], v["radii"])
+        a2.extra += float(rank + 1)
+        w_tail = a2.allreduce_extra_async()
+        w_main = a2.allreduce_main_async()
+        a2.wait(w_tail)
+        a2.wait(w_main)
+        assert torch.allclose(_cat(a2), _cat(arena), atol=1e-5) and torch.allclose(a2.stats, arena.stats, atol=1e-5)
+        assert torch.equal(a2.max_radii, arena.max_radii)
+        assert torch.equal(a2.extra, torch.full((44,), float(sum(range(1, world + 1)))))
+        a3 = parallel.GradArena.create(P, "cpu", extra_floats=8)      # ... and as the ONE blocking collective
+        a3.flat.fill_(1.0)
+        a3.allreduce()
+        assert torch.equal(a3.flat, torch.full_like(a3.flat, float(world)))
         # numpy arrays travel through the queue BY VALUE; torch tensors would go through shared-memory file descriptors
         # that vanish when this process exits before the parent has read them (ConnectionResetError)
         q.put((rank, seen, _cat(arena).numpy(), arena.stats.numpy().copy(), arena.max_radii.numpy().copy(),
@@ -97,6 +116,19 @@ def test_single_process_is_the_plain_sum():
     assert torch.allclose(_cat(arena), flat, atol=1e-5) and torch.allclose(arena.stats, stats, atol=1e-5)
     assert torch.equal(arena.max_radii, mx)
     assert parallel.shard_views(10, 3, 4) == [3, 7]
+
+
+def test_cost_balanced_view_assignment():
+    costs = [9.0, 1.0, 8.0, 2.0, 7.0, 3.0, 6.0, 4.0]
+    parts = parallel.assign_views_balanced(costs, 4)
+    assert sorted(i for p in parts for i in p) == list(range(8)) and all(len(p) == 2 for p in parts)
+    loads = [sum(costs[i] for i in p) for p in parts]
+    assert max(loads) - min(loads) <= 1e-9              # 9+1, 8+2, 7+3, 6+4
+    rr = [sum(costs[i] for i in parallel.shard_views(8, r, 4)) for r in range(4)]
+    assert max(rr) - min(rr) > 5.0                      # round-robin would leave one rank with 9+7 against 1+3
+    uneven = parallel.assign_views_balanced([5.0, 4.0, 3.0, 2.0, 1.0], 2)
+    assert sorted(len(p) for p in uneven) == [2, 3] and sorted(i for p in uneven for i in p) == list(range(5))
+    assert parallel.assign_views_balanced(costs, 1) == [[0, 2, 4, 6, 7, 5, 3, 1]]
 
 
 def test_bound_arena_receives_autograd_accumulation_in_place():

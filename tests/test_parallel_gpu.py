@@ -21,7 +21,7 @@ def test_densify_stats_kernel_matches_torch():
         radii = torch.randint(-3, 40, (P,), generator=g, dtype=torch.int32).clamp_min(0)
         arena.accumulate_view({}, vg.to(dev), radii.to(dev))
         vis = radii > 0
-        stats[:, 0] += torch.linalg.norm(vg[:, :2], dim=-1) * vis
+        stats[:, 0] += torch.linalg.norm(vg, dim=-1) * vis
         stats[:, 1] += vis.float()
         mx = torch.maximum(mx, radii)
     assert torch.allclose(arena.stats.cpu(), stats, rtol=1e-6, atol=1e-6)

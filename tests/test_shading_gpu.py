@@ -25,7 +25,8 @@ def _rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-20)).item()
 
 
-@pytest.mark.parametrize("H,W,res,srgb,view", [(120, 160, 64, False, 1), (97, 131, 128, True, 4), (64, 64, 32, False, 6)])
+@pytest.mark.parametrize("H,W,res,srgb,view", [(120, 160, 64, False, 1), (97, 131, 128, True, 4), (64, 64, 32, False, 6),
+                                               (800, 800, 512, False, 2)])   # BASELINE C1/C3: 800^2, 6 x 512^2, 6 levels
 def test_shade_forward_backward(H, W, res, srgb, view):
     from materialrefgs_b200.shading import shade_surfel
     cam = synthetic.orbit_camera(view, 8, W, H)
@@ -33,7 +34,18 @@ def test_shade_forward_backward(H, W, res, srgb, view):
     if view == 6:   # drive roughness outside [min_r, 1] and N.V outside [0,1] to hit the clamps
         feats[1] = feats[1] * 1.6 - 0.3
         allmap[2:5] = -allmap[2:5]
-    levels = so.synthetic_chain(res, 16, device=DEV)
+    if res == 512:
+        # BASELINE size: the chain the shader is fed in C1/C3 = EnvLight.build_mips of a 6x512^2 logit cubemap ~ N(0,1)
+        # (GGX-prefiltered levels; white-noise texels at 512^2 would make the fp32 rounding of u*512 itself worth 1e-4)
+        from materialrefgs_b200.shading import EnvLight
+        env0 = EnvLight(device=DEV, max_res=512, min_res=16, trainable=False)
+        with torch.no_grad():
+            env0.base.copy_(torch.randn(6, 512, 512, 3, generator=torch.Generator().manual_seed(1234)).to(DEV))
+        env0.build_mips()
+        levels = [l.detach().clone() for l in env0.specular]
+        assert len(levels) == 6
+    else:
+        levels = so.synthetic_chain(res, 16, device=DEV)
     bg = torch.tensor([0.2, 0.4, 0.6], device=DEV)
     g = torch.Generator().manual_seed(3)
     wts = {k: torch.randn(3, H, W, generator=g).to(DEV) for k in ("render", "specular_map", "diffuse_map", "rend_normal")}
@@ -54,10 +66,20 @@ def test_shade_forward_backward(H, W, res, srgb, view):
 
     for k in ("render", "specular_map", "diffuse_map", "rend_normal", "direct_light"):
         assert (out[k] - ref[k]).abs().max().item() <= 1e-4, k
-    assert _rel(b_m.grad, b_o.grad) <= 1e-3
-    assert _rel(f_m.grad[:5], f_o.grad[:5]) <= 1e-3
+
+    def close(a, b):
+        if res < 512:
+            return _rel(a, b) <= 1e-3
+        # 640 000 pixels looking up a 512^2 chain: a few dozen land within fp32 rounding of a texel-cell / mip-level
+        # boundary, where the fetch has two one-sided derivatives and either implementation may take either
+        # (tests/test_texture_properties_gpu.py checks the derivative away from the kinks). Bar: 1e-3 of the max-norm on
+        # all but 0.05 % of the elements.
+        bad = ((a - b).abs() > 1e-3 * b.abs().max()).float().mean().item()
+        return bad <= 5e-4
+    assert close(b_m.grad, b_o.grad)
+    assert close(f_m.grad[:5], f_o.grad[:5])
     assert not f_m.grad[5:].any()
-    assert _rel(a_m.grad[1:5], a_o.grad[1:5]) <= 1e-3
+    assert close(a_m.grad[1:5], a_o.grad[1:5])
     for lm, lo in zip(lv_m, lv_o):
         assert _rel(lm.grad, lo.grad) <= 1e-3
 
@@ -280,3 +302,33 @@ def test_per_surfel_volume_colours_forward_backward():
     assert _rel(odm, rdm) <= 1e-3
     for a, b in zip(olv, rlv):
         assert _rel(a, b) <= 1e-3
+
+
+def test_cubemap_gradient_through_build_mips_sink_equals_autograd():
+    """The trainable base cubemap receives its gradient through EnvLight.build_mips either by autograd (texel gradients
+    returned by the shading backward -> _BuildMips.backward) or through the multi-view sink (shading backward adds into
+    one [texels,4] buffer, flush_level_grads runs the prefilter backward once): same numbers, and twice the gradient for
+    two identical views."""
+    from materialrefgs_b200.shading import EnvLight, shade_surfel
+    H, W = 120, 160
+    cam = synthetic.orbit_camera(3, 8, W, H)
+    base, feats, allmap = so.synthetic_gbuffer(H, W, device=DEV, seed=2)
+    bg = torch.zeros(3, device=DEV)
+    env = EnvLight(device=DEV, max_res=128, min_res=16, trainable=True)
+    with torch.no_grad():
+        env.base.copy_(torch.randn(6, 128, 128, 3, generator=torch.Generator().manual_seed(21)).to(DEV))
+    w = torch.randn(3, H, W, generator=torch.Generator().manual_seed(22)).to(DEV)
+    env.build_mips()
+    assert env._chain is not None
+    (shade_surfel(env, base, feats, allmap, cam.HWK, cam.R, bg)["render"] * w).sum().backward()
+    auto = env.base.grad.clone()
+    assert float(auto.abs().max()) > 0
+    env.base.grad = None
+    env.build_mips()
+    env.enable_level_grad_sink()
+    base = base.requires_grad_(True)    # (in sink mode the texel gradients do not travel through autograd)
+    for _ in range(2):
+        (shade_surfel(env, base, feats, allmap, cam.HWK, cam.R, bg)["render"] * w).sum().backward()
+    assert env.base.grad is None            # nothing reaches the base before the flush
+    env.flush_level_grads()
+    assert _rel(env.base.grad, 2 * auto) <= 1e-5
