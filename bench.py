@@ -217,7 +217,12 @@ class StepBase:
             if self.free_events[k] is not None:
                 self.copy_stream.wait_event(self.free_events[k])   # the slot's previous consumer has finished
             cam = tuple(t.to(self.dev, non_blocking=True) for t in self.cam_host[view])
-            up = {n: t.to(self.dev, non_blocking=True) for n, t in self.up_host.items()} if self.train else {}
+            # per-view host input of a training step = the camera and ONE 3xHxW fp32 image (the ground-truth image in a
+            # real loop; here its stand-in, the photometric upstream gradient). The regularisers' gradient maps do not
+            # change from view to view and stay resident, like the surfel parameters.
+            up = dict(self.up)
+            if self.train:
+                up["render"] = self.up_host["render"].to(self.dev, non_blocking=True)
             self.in_events[k].record(self.copy_stream)
         self.in_slots[k] = (cam, up)
         self.pending = k
@@ -261,7 +266,7 @@ class StepBase:
         return self._e2e_consume(0) + self._e2e_consume(1)
 
     def h2d_bytes(self):
-        per_view = (16 + 16 + 3) * 4 + (sum(v.numel() * 4 for v in self.up_host.values()) if self.train else 0)
+        per_view = (16 + 16 + 3) * 4 + (self.up_host["render"].numel() * 4 if self.train else 0)
         return self.V * per_view
 
     def d2h_bytes(self):
@@ -272,6 +277,9 @@ class StepBase:
         pass
 
     def end_step(self):
+        pass
+
+    def finish_step(self):
         pass
 
     def render(self, view, cam_mats, up):
@@ -328,6 +336,11 @@ class OursStep(StepBase):
             self.env = EnvLight(device=dev, max_res=wl["cube_res"], min_res=wl["min_res"], trainable=self.train)
             with torch.no_grad():
                 self.env.base.copy_(self.base_init.to(dev))
+            if world > 1 and self.train:
+                # every rank filters 1/world of each level, one 25 MB allreduce assembles; on a communicator of its own
+                # so that these small collectives do not queue behind the step's big gradient allreduce
+                import torch.distributed as dist
+                self.env.shard_build_mips(dist.new_group())
             self.env.build_mips()
             texels = sum(l.shape[0] * l.shape[1] * l.shape[2] for l in self.env.specular)
         # ONE flat buffer: [parameter gradients | densification statistics | cubemap texel-gradient sink]; the segments
@@ -349,14 +362,24 @@ class OursStep(StepBase):
             if self.env is not None:
                 self.env.use_level_grad_sink(self.arena.extra.view(texels, 4))
 
+    pending = None     # the previous step's per-surfel gradient allreduce, still in flight
+
     def begin_step(self):
+        if self.env is not None and self.train:
+            self.env.base.grad = None
+            self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
         if self.train:
+            self.finish_step()                 # (an optimizer would consume the reduced surfel gradients here)
             self.arena.zero_()                 # one memset: gradients + statistics (+ the sink, zero after its flush)
             self.means2D.grad = None
-            if self.env is not None:
-                self.env.base.grad = None
-        if self.env is not None and self.train:
-            self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
+
+    def finish_step(self):
+        """Wait for the per-surfel gradient allreduce of the step just enqueued. It is left in flight across the step
+        boundary: the cubemap's own gradient (prefilter backward) and the NEXT step's build_mips only need the texel sink,
+        so they run under it; the surfel gradients are needed when the surfels are (updated and) rasterized again."""
+        if self.pending is not None:
+            self.arena.wait(self.pending)
+            self.pending = None
 
     def render(self, view, cam_mats, up, last=False):
         c = self.cam_dev[view]
@@ -367,7 +390,8 @@ class OursStep(StepBase):
             for dst, src in zip(slots, cam_mats):
                 dst.copy_(src, non_blocking=True)
             for k, v in up.items():
-                self.up[k].copy_(v, non_blocking=True)
+                if v is not self.up[k]:
+                    self.up[k].copy_(v, non_blocking=True)
         busy = getattr(self, "out_busy", {}).pop(view, None)
         if busy is not None:                 # the graph's output tensors are still being copied to the host
             torch.cuda.current_stream(self.dev).wait_event(busy)
@@ -443,6 +467,7 @@ class OursStep(StepBase):
             c = self.cam_dev[v]
             self.render(v, (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up)
         self.end_step()
+        self.finish_step()
         torch.cuda.synchronize()
         self.graphs.check()
 
@@ -460,12 +485,13 @@ class OursStep(StepBase):
             # which only needs the texel-gradient sink (reduced above, under the last view's rasterizer backward)
             if self.env is not None and getattr(self, "sink_work", None) is None:
                 self.sink_work = self.arena.allreduce_extra_async()   # (graph replay: no hook inside the last view)
-            work = self.arena.allreduce_main_async()
+            self.pending = self.arena.allreduce_main_async()
             if self.env is not None:
                 self.arena.wait(self.sink_work)
                 self.sink_work = None
                 self.env.flush_level_grads()
-            self.arena.wait(work)
+            else:
+                self.finish_step()
         elif self.env is not None:
             self.env.flush_level_grads()
 
@@ -699,6 +725,7 @@ def main():
         stepper.prime_graphs()
     for i in range(a.warmup):
         stepper.step(i)
+    stepper.finish_step()
     barrier(world)
     if ours:
         stepper.lib.mrgs_profile_reset()
@@ -712,6 +739,7 @@ def main():
         stepper.step(a.warmup + i)
         if graphs and i % 4 == 3:
             stepper.lib.mrgs_profile_collect_captured()   # one sample per captured stage (waits for this step's last view)
+    stepper.finish_step()         # the last step's gradient allreduce completes inside the timed region
     e1.record()
     barrier(world)
     ms = e0.elapsed_time(e1)
@@ -736,10 +764,12 @@ def main():
     for i in range(2):
         stepper.step(i, e2e=True)
     stepper.e2e_finish()
+    stepper.finish_step()
     barrier(world)
     t0 = time.perf_counter()
     for i in range(a.steps):
         stepper.step(a.warmup + i, e2e=True)
+    stepper.finish_step()
     stepper.e2e_finish()          # the last step's results are read inside the timed region too
     barrier(world)
     e2e_ms = (time.perf_counter() - t0) * 1000.0 / a.steps
@@ -762,7 +792,8 @@ def main():
     par = f"view-sharded x{world}"
     if world > 1 and stepper.train:
         par += (" + ONE NCCL sum-allreduce of the flat [P*68-float gradient+statistics arena | cubemap texel-gradient sink] buffer "
-                "(sink part issued under the last view's rasterizer backward, arena part overlapped with the build_mips backward) "
+                "(sink part issued under the last view's rasterizer backward; surfel part left in flight under the prefilter backward and the next "
+                "step's build_mips, both of which are sharded over the ranks and use a communicator of their own) "
                 "+ one int32 max-allreduce of max_radii2D; views dealt to ranks by cost (LPT on last-seen instance counts)")
     line = {
         "metric": wl["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
@@ -776,7 +807,8 @@ def main():
                          "arenas + 2 x 5 GB of prefilter weights streamed once per step) exceeds the 126 MB L2"},
         "e2e": {"value": views_per_step * 1000.0 / e2e_ms, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                 "d2h_bytes_per_step": d2h_bytes,
-                "note": "per step: camera + upstream-gradient maps copied from pinned host memory, rendered image and loss of every "
+                "note": "per view: camera + one 3xHxW fp32 image (the ground-truth image's stand-in: the photometric upstream gradient) "
+                        "copied from pinned host memory - the regularisers' gradient maps are view-invariant and resident -, rendered image and loss of every "
                         "view read back to pinned host memory and consumed by the host one step later (double-buffered, like "
                         "asynchronous logging), the last step's before the clock stops; surfel parameters and the cubemap are "
                         "model state resident in HBM"},

@@ -40,7 +40,8 @@
  * ABI history: 5 = gradient sink (accumulate) in mrgs_backward; 6 = mrgs_geometry_loss_*, mrgs_img_grad_weight,
  * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query;
  * 7 = prefilter plans (mrgs_prefilter_*), mrgs_mip_pyramid_forward, mrgs_mip_chain_backward;
- * 8 = MrgsForwardArgs.no_wait / count_out (capture-safe forward), mrgs_profile_collect_captured.
+ * 8 = MrgsForwardArgs.no_wait / count_out (capture-safe forward), mrgs_profile_collect_captured;
+ * 9 = MrgsPrefilterJob.patch_begin / patch_end.
  */
 #ifndef MRGS_H_INCLUDED
 #define MRGS_H_INCLUDED
@@ -52,7 +53,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 8
+#define MRGS_ABI_VERSION 9
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -458,6 +459,10 @@ typedef struct MrgsPrefilterJob {
     const float* nan_where_zero;
     int32_t src_stride;
     int32_t dst_stride;
+    /* patches [patch_begin, patch_end) of the plan only (0, 0 = all): a rank of a view-sharded step applies its share
+     * of every level into a zero-filled buffer and the ranks sum the buffers (materialrefgs_b200/prefilter.py) */
+    int32_t patch_begin;
+    int32_t patch_end;
 } MrgsPrefilterJob;
 
 /* number of patches (= warps of the gather), or -1 when the shape does not tile a res x res face */

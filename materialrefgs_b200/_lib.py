@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 8
+MRGS_ABI_VERSION = 9
 MAX_FEATURES = 24
 TILE = 16
 
@@ -141,7 +141,7 @@ class PrefilterBuildArgs(C.Structure):
 
 class PrefilterJob(C.Structure):
     _fields_ = [("plan", PrefilterPlan), ("src", _fp), ("dst", _fp), ("nan_where_zero", _fp),
-                ("src_stride", C.c_int32), ("dst_stride", C.c_int32)]
+                ("src_stride", C.c_int32), ("dst_stride", C.c_int32), ("patch_begin", C.c_int32), ("patch_end", C.c_int32)]
 
 
 SYMBOLS = {

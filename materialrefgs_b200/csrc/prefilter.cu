@@ -254,7 +254,7 @@ struct GatherJob {
     const float* src;
     float* dst;
     const float* nan_where_zero;
-    int N, G, pwl, texels, src_stride, dst_stride;
+    int N, G, pwl, texels, src_stride, dst_stride, patch_begin;
 };
 struct GatherParams {
     GatherJob job[kMaxJobs];
@@ -442,7 +442,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) prefilter_gather_kernel(con
     }
     if (k >= p.num_jobs) return;
     const GatherJob& j = p.job[k];
-    const int patch = warp - first;
+    const int patch = j.patch_begin + (warp - first);
     if (j.G == 1) {
         if (j.src_stride == 4) gather_patch<1, 4>(j, patch, lane, ring, bars);
         else gather_patch<1, 3>(j, patch, lane, ring, bars);
@@ -614,7 +614,11 @@ int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, cudaStrea
         j.texels = 6 * s.plan.res * s.plan.res;
         j.src_stride = s.src_stride;
         j.dst_stride = s.dst_stride;
-        warps += prefilter_patch_count(s.plan.res, s.plan.rows_per_lane, s.plan.patch_width);
+        const int all = prefilter_patch_count(s.plan.res, s.plan.rows_per_lane, s.plan.patch_width);
+        const bool sub = s.patch_end > s.patch_begin;
+        if (sub && (s.patch_begin < 0 || s.patch_end > all)) return MRGS_ERR_INVALID_ARGUMENT;
+        j.patch_begin = sub ? s.patch_begin : 0;
+        warps += sub ? s.patch_end - s.patch_begin : all;
         p.warp_end[k] = warps;
     }
     p.num_jobs = num_jobs;

@@ -245,19 +245,30 @@ def plan_pair(kind: str, res: int, roughness: float, ct: float | None, device, s
     return fwd, bwd
 
 
-def apply_jobs(jobs, backward: bool, device) -> None:
+def apply_jobs(jobs, backward: bool, device, shard=None) -> None:
     """jobs: list of (plan, src, src_stride, dst, dst_stride, nan_where_zero or None); ONE launch per 8 jobs,
-    longest tap lists first."""
+    longest tap lists first. shard = (rank, world): only this rank's contiguous share of every plan's patches."""
     lib = _lib.load()
     jobs = sorted(jobs, key=lambda j: -(j[0].rows / max(j[0].patches, 1)))
+    if shard is not None:
+        rank, world = shard
+        ranged = []
+        for j in jobs:
+            n = j[0].patches
+            b, e = n * rank // world, n * (rank + 1) // world
+            if e > b:
+                ranged.append((*j, b, e))
+        jobs = ranged
     for i in range(0, len(jobs), _lib.PREFILTER_MAX_JOBS):
         chunk = jobs[i:i + _lib.PREFILTER_MAX_JOBS]
         arr = (_lib.PrefilterJob * len(chunk))()
-        for k, (plan, src, ss, dst, ds, nz) in enumerate(chunk):
+        for k, (plan, src, ss, dst, ds, nz, *rng) in enumerate(chunk):
             arr[k].plan = plan.struct()
             arr[k].src, arr[k].dst = src.data_ptr(), dst.data_ptr()
             arr[k].nan_where_zero = None if nz is None else nz.data_ptr()
             arr[k].src_stride, arr[k].dst_stride = ss, ds
+            if rng:
+                arr[k].patch_begin, arr[k].patch_end = rng
         with torch.cuda.device(device):
             _lib.check(lib.mrgs_prefilter_apply(arr, len(chunk), int(backward), _stream(device)), "mrgs_prefilter_apply")
 
@@ -296,10 +307,13 @@ class MipChain:
 
     _static = None
 
-    def forward(self, base: torch.Tensor, static: bool = False):
+    def forward(self, base: torch.Tensor, static: bool = False, shard=None):
         """base [6,res,res,3] -> ([prefiltered level l: [6,res>>l,res>>l,3]], diffuse [6,rmin,rmin,3]).
         static: write into the chain's own persistent output buffers (every call returns tensors over the SAME storage),
-        which is what consumers captured in a CUDA graph need."""
+        which is what consumers captured in a CUDA graph need.
+        shard = (rank, world, group): view-sharded steps replicate the cubemap on every rank; instead of every rank
+        filtering all of it, each applies its share of every level's patches and ONE allreduce assembles the chain
+        (every rank must call)."""
         lib = _lib.load()
         dev = self.device
         base = base.detach().contiguous()
@@ -308,29 +322,38 @@ class MipChain:
             _lib.check(lib.mrgs_mip_pyramid_forward(base.data_ptr(), self.res, self.n, _ptr_array(raw), _stream(dev)),
                        "mrgs_mip_pyramid_forward")
         if static and self._static is not None:
-            levels, diffuse = self._static
+            levels, diffuse, flat = self._static
         else:
-            levels = [torch.empty((6, r, r, 3), dtype=torch.float32, device=dev) for r in self.sizes]
-            diffuse = torch.empty((6, self.sizes[-1], self.sizes[-1], 3), dtype=torch.float32, device=dev)
+            # one flat buffer for all outputs: a sharded build sums it across ranks with ONE collective
+            n_d = 6 * self.sizes[-1] * self.sizes[-1]
+            flat = torch.empty((self.texels + n_d, 3), dtype=torch.float32, device=dev)
+            levels = [flat[self.offsets[l]:self.offsets[l + 1]].view(6, r, r, 3) for l, r in enumerate(self.sizes)]
+            diffuse = flat[self.texels:].view(6, self.sizes[-1], self.sizes[-1], 3)
             if static:
-                self._static = (levels, diffuse)
+                self._static = (levels, diffuse, flat)
+        if shard is not None:
+            flat.zero_()
         jobs = [(self.spec[l][0], raw[l], 4, levels[l], 3, self.spec[l][0].wsum) for l in range(self.n)]
         jobs.append((self.diff[0], raw[-1], 4, diffuse, 3, None))
-        apply_jobs(jobs, False, dev)
+        apply_jobs(jobs, False, dev, None if shard is None else shard[:2])
+        if shard is not None:
+            # every rank filtered its share of every level's patches into the zero-filled buffer: the sum is the chain
+            # (x + 0 is exact, so the result equals the unsharded build bit for bit)
+            import torch.distributed as dist
+            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=shard[2])
         return levels, diffuse
 
-    def backward(self, grad4: torch.Tensor | None, grad_diffuse: torch.Tensor | None) -> torch.Tensor:
+    def backward(self, grad4: torch.Tensor | None, grad_diffuse: torch.Tensor | None, shard=None) -> torch.Tensor:
         """grad4: [texels,4] gradient of the prefiltered levels (rgb + pad, level after level: the layout of
         EnvLight.level_grad_sink), grad_diffuse [6,rmin,rmin,3]; returns the gradient of the base cubemap."""
         lib = _lib.load()
         dev = self.device
-        g0 = torch.empty((6, self.res, self.res, 3), dtype=torch.float32, device=dev)
-        rest = torch.empty((self.texels - self.counts[0] + 1, 3), dtype=torch.float32, device=dev)
-        grads = [g0]
-        off = 0
-        for l in range(1, self.n):
-            grads.append(rest[off:off + self.counts[l]].view(6, self.sizes[l], self.sizes[l], 3))
-            off += self.counts[l]
+        n_d = 6 * self.sizes[-1] * self.sizes[-1]
+        gflat = torch.empty((self.texels + n_d, 3), dtype=torch.float32, device=dev)
+        grads = [gflat[self.offsets[l]:self.offsets[l + 1]].view(6, r, r, 3) for l, r in enumerate(self.sizes)]
+        g0 = grads[0]
+        if shard is not None:
+            gflat.zero_()
         jobs = []
         if grad4 is not None:
             if tuple(grad4.shape) != (self.texels, 4) or not grad4.is_contiguous():
@@ -342,10 +365,13 @@ class MipChain:
                 g.zero_()
         extra = None
         if grad_diffuse is not None:
-            extra = torch.empty_like(grads[-1])
+            extra = gflat[self.texels:].view(6, self.sizes[-1], self.sizes[-1], 3)
             jobs.append((self.diff[1], grad_diffuse.contiguous(), 3, extra, 3, None))
         if jobs:
-            apply_jobs(jobs, True, dev)
+            apply_jobs(jobs, True, dev, None if shard is None else shard[:2])
+            if shard is not None:      # the ranks' shares of d(raw levels) (+ the diffuse map's) in ONE collective
+                import torch.distributed as dist
+                dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=shard[2])
         if self.n == 1 and extra is not None:
             g0.add_(extra)
         with torch.cuda.device(dev):
@@ -370,9 +396,9 @@ class _BuildMips(torch.autograd.Function):
     """base -> (level 0, ..., level n-1, diffuse): EnvLight.build_mips (scene/light.py:72-86) as one autograd node."""
 
     @staticmethod
-    def forward(ctx, base, chain: MipChain, static: bool = False):
-        levels, diffuse = chain.forward(base, static)
-        ctx.chain = chain
+    def forward(ctx, base, chain: MipChain, static: bool = False, shard=None):
+        levels, diffuse = chain.forward(base, static, shard)
+        ctx.chain, ctx.shard = chain, shard
         ctx.set_materialize_grads(False)
         if static:      # fresh tensor objects over the persistent storage (an autograd output must not be reused)
             levels, diffuse = [t.view(t.shape) for t in levels], diffuse.view(diffuse.shape)
@@ -383,16 +409,16 @@ class _BuildMips(torch.autograd.Function):
         chain: MipChain = ctx.chain
         g_levels, g_diffuse = grads[:-1], grads[-1]
         if g_diffuse is None and all(g is None for g in g_levels):
-            return None, None, None  # e.g. the texel gradients went to EnvLight's sink instead of through autograd
+            return None, None, None, None  # e.g. the texel gradients went to EnvLight's sink instead of through autograd
         grad4 = None
         if any(g is not None for g in g_levels):
             grad4 = torch.zeros((chain.texels, 4), dtype=torch.float32, device=chain.device)
             for l, g in enumerate(g_levels):
                 if g is not None:
                     grad4[chain.offsets[l]:chain.offsets[l + 1], :3] = g.reshape(-1, 3)
-        return chain.backward(grad4, g_diffuse), None, None
+        return chain.backward(grad4, g_diffuse, ctx.shard), None, None, None
 
 
-def build_mips(base, chain: MipChain, static: bool = False):
-    outs = _BuildMips.apply(base, chain, static)
+def build_mips(base, chain: MipChain, static: bool = False, shard=None):
+    outs = _BuildMips.apply(base, chain, static, shard)
     return list(outs[:-1]), outs[-1]

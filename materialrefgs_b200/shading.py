@@ -392,6 +392,24 @@ class EnvLight(torch.nn.Module):
         self.build_mips()
 
     _chain = None
+    shard_world = None      # set by shard_build_mips(): (group,) - build_mips forward/backward split over its ranks
+
+    def shard_build_mips(self, group=None):
+        """View-sharded training replicates the cubemap on every rank. After this call every rank filters only its share
+        of each level (forward) / of each level's gradient (backward) and one allreduce of the 25 MB chain assembles the
+        result - identical numbers, 1/world of the work. Collective: every rank of `group` must call build_mips() and
+        flush_level_grads() / backward together."""
+        self.shard_world = (group,)
+
+    def _shard(self):
+        if self.shard_world is None:
+            return None
+        import torch.distributed as dist
+        group = self.shard_world[0]
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return None
+        return dist.get_rank(group), dist.get_world_size(group), group
+
     static_chain = False    # True: build_mips() rewrites the SAME level buffers every time (CUDA-graph consumers, graphs.py)
 
     def chain_roughnesses(self, n):
@@ -420,7 +438,7 @@ class EnvLight(torch.nn.Module):
             except pf.PrefilterTooLarge:
                 self._chain = None
         if self._chain is not None:
-            self.specular, self.diffuse = pf.build_mips(self.base, self._chain, self.static_chain)
+            self.specular, self.diffuse = pf.build_mips(self.base, self._chain, self.static_chain, self._shard())
         else:
             self.specular = [self.base]
             while self.specular[-1].shape[1] > self.min_res:
@@ -474,7 +492,7 @@ class EnvLight(torch.nn.Module):
             return
         if self._chain is not None:
             if self.base.requires_grad:
-                g = self._chain.backward(sink, None)
+                g = self._chain.backward(sink, None, self._shard())
                 self.base.grad = g if self.base.grad is None else self.base.grad.add_(g)
         else:
             flat3 = sink[:, :3].contiguous()
