@@ -362,7 +362,7 @@ class OursStep(StepBase):
             if self.env is not None:
                 self.env.use_level_grad_sink(self.arena.extra.view(texels, 4))
 
-    pending = None     # the previous step's per-surfel gradient allreduce, still in flight
+    inflight = None    # the previous step's per-surfel gradient allreduce, still in flight
 
     def begin_step(self):
         if self.env is not None and self.train:
@@ -377,9 +377,9 @@ class OursStep(StepBase):
         """Wait for the per-surfel gradient allreduce of the step just enqueued. It is left in flight across the step
         boundary: the cubemap's own gradient (prefilter backward) and the NEXT step's build_mips only need the texel sink,
         so they run under it; the surfel gradients are needed when the surfels are (updated and) rasterized again."""
-        if self.pending is not None:
-            self.arena.wait(self.pending)
-            self.pending = None
+        if self.inflight is not None:
+            self.arena.wait(self.inflight)
+            self.inflight = None
 
     def render(self, view, cam_mats, up, last=False):
         c = self.cam_dev[view]
@@ -485,7 +485,7 @@ class OursStep(StepBase):
             # which only needs the texel-gradient sink (reduced above, under the last view's rasterizer backward)
             if self.env is not None and getattr(self, "sink_work", None) is None:
                 self.sink_work = self.arena.allreduce_extra_async()   # (graph replay: no hook inside the last view)
-            self.pending = self.arena.allreduce_main_async()
+            self.inflight = self.arena.allreduce_main_async()
             if self.env is not None:
                 self.arena.wait(self.sink_work)
                 self.sink_work = None
