@@ -331,14 +331,27 @@ class OursStep(StepBase):
         self._lib, self.lib = _lib, _lib.load()
         self.GRS, self.GR, self.shade = GaussianRasterizationSettings, GaussianRasterizer, shade_surfel
         self.env = None
+        self.overlap = False
+        self.shard_mips = False
         texels = 0
         if wl["shade"]:
             self.env = EnvLight(device=dev, max_res=wl["cube_res"], min_res=wl["min_res"], trainable=self.train)
             with torch.no_grad():
                 self.env.base.copy_(self.base_init.to(dev))
-            if world > 1 and self.train:
-                # every rank filters 1/world of each level, one 25 MB allreduce assembles; on a communicator of its own
-                # so that these small collectives do not queue behind the step's big gradient allreduce
+            # (single GPU only: the phase-ordered step has not been run under NCCL)
+            self.overlap = bool(wl.get("overlap")) and self.train and world == 1
+            if self.overlap:
+                # build_mips forward/backward (HBM-bound gathers) run on a second stream with one CTA per SM, in the
+                # background of the issue-bound tile-blend kernels (EnvLight.run_in_background)
+                self.env.run_in_background(ctas_per_sm=float(os.environ.get("MRGS_BG_CTAS_PER_SM", "1")))
+            # EXPERIMENTAL, off by default (MRGS_BENCH_SHARD_MIPS=1): every rank filters 1/world of each level and one 25 MB
+            # allreduce assembles the chain, on a communicator of its own, with the step's big gradient allreduce left in
+            # flight across the step boundary. Bit-equal to the replicated build (tools/shard_check.py) and 10 % faster
+            # at 2 GPUs (729 vs 665 frames/s), but the 8-GPU run of this scheme DEADLOCKED (two communicators in flight
+            # at once) and the GPU budget ended before the cause was found: the default is the configuration measured
+            # at 8 GPUs - replicated build_mips, one communicator, the allreduce completed inside its own step.
+            self.shard_mips = world > 1 and self.train and os.environ.get("MRGS_BENCH_SHARD_MIPS", "0") == "1"
+            if self.shard_mips:
                 import torch.distributed as dist
                 self.env.shard_build_mips(dist.new_group())
             self.env.build_mips()
@@ -365,13 +378,22 @@ class OursStep(StepBase):
     inflight = None    # the previous step's per-surfel gradient allreduce, still in flight
 
     def begin_step(self):
-        if self.env is not None and self.train:
+        if self.shard_mips:                    # experimental ordering: build_mips runs under the in-flight allreduce
             self.env.base.grad = None
-            self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
-        if self.train:
+            self.env.build_mips()
             self.finish_step()                 # (an optimizer would consume the reduced surfel gradients here)
+            self.arena.zero_()
+            self.means2D.grad = None
+            return
+        if self.overlap:
+            self.env.sync()                    # the previous step's background build_mips backward still reads the sink
+        if self.train:
             self.arena.zero_()                 # one memset: gradients + statistics (+ the sink, zero after its flush)
             self.means2D.grad = None
+            if self.env is not None:
+                self.env.base.grad = None
+        if self.env is not None and self.train:
+            self.env.build_mips()              # every iteration, like train_refnerf.py:1155-1163
 
     def finish_step(self):
         """Wait for the per-surfel gradient allreduce of the step just enqueued. It is left in flight across the step
@@ -380,6 +402,8 @@ class OursStep(StepBase):
         if self.inflight is not None:
             self.arena.wait(self.inflight)
             self.inflight = None
+        if self.overlap:
+            self.env.sync()                    # background work of the step belongs to the step (and to its timing)
 
     def render(self, view, cam_mats, up, last=False):
         c = self.cam_dev[view]
@@ -444,6 +468,76 @@ class OursStep(StepBase):
         self.last = {"radii": radii, "render": image, "loss": loss}
         return loss
 
+    def step(self, i, e2e=False):
+        if not self.overlap:
+            return super().step(i, e2e)
+        # Phase-ordered step (same arithmetic as view after view; gradients are sums either way):
+        #   F1  rasterizer forward of every view          | build_mips forward in the background (second stream)
+        #   F2  shading forward + backward of every view  -> dL/dG-buffers, cubemap texel gradients in the sink
+        #   B   rasterizer backward of every view         | build_mips backward in the background
+        views = self.views_for_step(i)
+        self.begin_step()
+        L, wl = self.leaves, self.wl
+        if e2e and views and getattr(self, "prefetched_step", None) != i:
+            self._e2e_prefetch(views[0])
+        gbuf = []
+        for v, view in enumerate(views):
+            if e2e:
+                cam_mats, up = self._e2e_take()
+                if v + 1 < len(views):
+                    self._e2e_prefetch(views[v + 1])
+                else:
+                    nxt = self.views_for_step(i + 1)
+                    if nxt:
+                        self._e2e_prefetch(nxt[0])
+                        self.prefetched_step = i + 1
+            else:
+                c = self.cam_dev[view]
+                cam_mats, up = (c.world_view_transform, c.full_proj_transform, c.camera_center), self.up
+            cam = self.cams[view]
+            rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, cam_mats[0], cam_mats[1],
+                          wl["sh_degree"], cam_mats[2], False, False)
+            rast = self.GR(rs, grad_sink=self.sink)
+            m2 = torch.zeros_like(self.means2D, requires_grad=True) if self.world > 1 else self.means2D
+            _, color, feat, radii, allmap = rast(means3D=L["means3D"], means2D=m2, opacities=L["opacities"], shs=L["shs"],
+                                                 features=L["features"], scales=L["scales"], rotations=L["rotations"])
+            if getattr(rast, "num_rendered", None):
+                self.cost[view] = float(rast.num_rendered)
+            gbuf.append((view, cam, up, color, feat, allmap, radii, m2, self.taken if e2e else None))
+        grads = []
+        for v, (view, cam, up, color, feat, allmap, radii, m2, slot) in enumerate(gbuf):
+            c_l, f_l, a_l = (t.detach().requires_grad_(True) for t in (color, feat, allmap))
+            out = self.shade(self.env, c_l, f_l, a_l, cam.HWK, cam.R, self.bg)
+            image, normal = out["render"], out["rend_normal"]
+            loss = (image.detach() * up["render"]).sum()
+            torch.autograd.backward([image, normal], [up["render"], up["normal"]])
+            grads.append((c_l.grad, f_l.grad, a_l.grad.add_(up["allmap"])))   # + the regularisers' own allmap gradient
+            self.last = {"radii": radii, "render": image, "loss": loss}
+            if e2e:
+                self.taken, self.last_view = slot, view
+                self._e2e_readback(i & 1, v, loss)
+        # every view's texel gradients are in the sink: the cubemap's backward starts now, under the rasterizer backwards
+        if self.world > 1:
+            self.sink_work = self.arena.allreduce_extra_async()
+            with torch.cuda.stream(self.env.background[0]):
+                self.env.background[0].wait_stream(torch.cuda.current_stream(self.dev))
+                self.arena.wait(self.sink_work)
+            self.sink_work = None
+        self.env.flush_level_grads()
+        for (view, cam, up, color, feat, allmap, radii, m2, slot), g in zip(gbuf, grads):
+            m2.grad = None
+            torch.autograd.backward([color, feat, allmap], list(g))
+            if self.world > 1:
+                self.arena.accumulate_view({}, m2.grad, radii)
+        total = None
+        if e2e:
+            self.result_events[i & 1].record(self.copy_stream)
+            total = self._e2e_consume((i & 1) ^ 1)
+            self.result_pending[i & 1] = True
+        if self.world > 1:
+            self.inflight = self.arena.allreduce_main_async()
+        return total
+
     def measure_costs(self):
         """Instance count R of every camera from one forward-only rasterization (untimed set-up)."""
         L = self.leaves
@@ -490,8 +584,8 @@ class OursStep(StepBase):
                 self.arena.wait(self.sink_work)
                 self.sink_work = None
                 self.env.flush_level_grads()
-            else:
-                self.finish_step()
+            if not self.shard_mips:
+                self.finish_step()             # the step's allreduce completes inside the step
         elif self.env is not None:
             self.env.flush_level_grads()
 
@@ -666,6 +760,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--P", type=int, default=None, help="override the surfel count (debug only)")
     ap.add_argument("--views-per-rank", type=int, default=None)
+    ap.add_argument("--overlap", type=int, default=0,
+                    help="1: phase-ordered step - all rasterizer forwards, all shading forward+backward, all rasterizer "
+                         "backwards - with build_mips forward/backward running in the background of the rasterizer phases "
+                         "on a second stream (EnvLight.run_in_background). Measured at C3: same gradients, 348 frames/s end "
+                         "to end against 350 view after view - the HBM-bound gather does not hide behind the issue-bound "
+                         "blend kernels, it takes SM slots from them - hence off")
     ap.add_argument("--graphs", type=int, default=0,
                     help="1: replay every view as a CUDA graph (materialrefgs_b200/graphs.py); measured at C3: +0.7 %% device-timed, "
                          "-6.5 %% end to end against eager launches (the host already runs ahead of the GPU), hence off")
@@ -676,6 +776,7 @@ def main():
     if a.P:
         wl["P"] = a.P
     wl["graphs"] = bool(a.graphs)
+    wl["overlap"] = bool(a.overlap) and not a.graphs
     a.warmup = max(a.warmup, 3)
 
     if not torch.cuda.is_available():
@@ -792,8 +893,7 @@ def main():
     par = f"view-sharded x{world}"
     if world > 1 and stepper.train:
         par += (" + ONE NCCL sum-allreduce of the flat [P*68-float gradient+statistics arena | cubemap texel-gradient sink] buffer "
-                "(sink part issued under the last view's rasterizer backward; surfel part left in flight under the prefilter backward and the next "
-                "step's build_mips, both of which are sharded over the ranks and use a communicator of their own) "
+                "(sink part issued under the last view's rasterizer backward, arena part overlapped with the build_mips backward) "
                 "+ one int32 max-allreduce of max_radii2D; views dealt to ranks by cost (LPT on last-seen instance counts)")
     line = {
         "metric": wl["metric"], "value": value, "unit": "frames/s", "n_gpus": world, "steps": a.steps,
@@ -865,6 +965,14 @@ def main():
         line["frame_roofline"] = {"algorithmic_bytes_per_frame": frame_bytes,
                                   "achieved_gbs": frame_bytes / (ms_per_frame * 1e-3) / 1e9,
                                   "frac": frame_bytes / (ms_per_frame * 1e-3) / 1e9 / peak}
+    if stepper.train and stepper.arena is not None:
+        # L1 norms of what the last step accumulated (same for every schedule of the same views up to atomics order)
+        if stepper.env is not None:
+            stepper.env.sync()
+        torch.cuda.synchronize()
+        line["grad_checksum"] = {"arena_l1": float(stepper.arena.main.double().abs().sum()),
+                                 "cubemap_l1": float(stepper.env.base.grad.double().abs().sum())
+                                 if stepper.env is not None and stepper.env.base.grad is not None else None}
     line["stage_ms"] = stage_ms
     line["stage_calls_per_step"] = {k: v / max(a.steps, 1) for k, v in stage_calls.items()}
     if not a.no_cpu_baseline and world == 1 and a.config == "C3":

@@ -41,7 +41,7 @@
  * mrgs_envlight_query_backward, mrgs_surfel_shade_*, single-level chains accepted by mrgs_envlight_query;
  * 7 = prefilter plans (mrgs_prefilter_*), mrgs_mip_pyramid_forward, mrgs_mip_chain_backward;
  * 8 = MrgsForwardArgs.no_wait / count_out (capture-safe forward), mrgs_profile_collect_captured;
- * 9 = MrgsPrefilterJob.patch_begin / patch_end.
+ * 9 = MrgsPrefilterJob.patch_begin / patch_end; 10 = mrgs_prefilter_apply(max_ctas).
  */
 #ifndef MRGS_H_INCLUDED
 #define MRGS_H_INCLUDED
@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define MRGS_ABI_VERSION 9
+#define MRGS_ABI_VERSION 10
 
 #if defined(__GNUC__)
 #define MRGS_API __attribute__((visibility("default")))
@@ -471,8 +471,12 @@ MRGS_API int mrgs_prefilter_texel_table(int32_t res, float* table, void* stream)
 MRGS_API int mrgs_prefilter_plan_count(const MrgsPrefilterBuildArgs* args, void* stream);
 MRGS_API int mrgs_prefilter_plan_fill(const MrgsPrefilterBuildArgs* args, void* stream);
 /* All jobs (at most MRGS_PREFILTER_MAX_JOBS: the levels of a chain + its diffuse map) in ONE launch, in the order
- * given (put the jobs with the longest tap lists first). backward != 0 only selects the profiling stage. */
-MRGS_API int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, void* stream);
+ * given (put the jobs with the longest tap lists first). backward != 0 only selects the profiling stage.
+ * max_ctas > 0 caps the grid (the warps then stride over the patches): the gather is HBM-bound and leaves most issue
+ * slots idle, the tile-blend kernels are the opposite - with e.g. one CTA per SM on a second stream the gather runs in
+ * their background instead of in front of them. 0 = one warp per patch. */
+MRGS_API int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, int32_t max_ctas,
+                                  void* stream);
 /* base [6][res][res][3] -> levels4[0] = float4-padded copy of it, levels4[l] = [6][res>>l][res>>l][4] 2x2 averages
  * (cubemap_mip forward, scene/light_utils.py:69-71, for the whole chain in one launch per 5 levels).
  * levels4 is a HOST array of num_levels device pointers; res must be divisible by 2^(num_levels-1). */

@@ -12,7 +12,7 @@ from pathlib import Path
 _PKG = Path(__file__).resolve().parent
 LIB_PATH = _PKG / "libmrgs.so"
 
-MRGS_ABI_VERSION = 9
+MRGS_ABI_VERSION = 10
 MAX_FEATURES = 24
 TILE = 16
 
@@ -182,7 +182,7 @@ SYMBOLS = {
     "mrgs_prefilter_texel_table": (C.c_int, [C.c_int32, _fp, C.c_void_p]),
     "mrgs_prefilter_plan_count": (C.c_int, [C.POINTER(PrefilterBuildArgs), C.c_void_p]),
     "mrgs_prefilter_plan_fill": (C.c_int, [C.POINTER(PrefilterBuildArgs), C.c_void_p]),
-    "mrgs_prefilter_apply": (C.c_int, [C.POINTER(PrefilterJob), C.c_int32, C.c_int32, C.c_void_p]),
+    "mrgs_prefilter_apply": (C.c_int, [C.POINTER(PrefilterJob), C.c_int32, C.c_int32, C.c_int32, C.c_void_p]),
     "mrgs_mip_pyramid_forward": (C.c_int, [_fp, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_void_p]),
     "mrgs_mip_chain_backward": (C.c_int, [C.c_int32, C.c_int32, C.POINTER(C.c_void_p), _fp, C.c_void_p]),
     "mrgs_forward": (C.c_int, [C.POINTER(ForwardArgs), C.c_void_p]),

@@ -892,7 +892,7 @@ int mrgs_prefilter_plan_fill(const MrgsPrefilterBuildArgs* a, void* stream_) {
     MRGS_LAUNCH_OK("prefilter_plan_fill", stream, false);
     return MRGS_OK;
 }
-int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, void* stream_) {
+int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t backward, int32_t max_ctas, void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     MRGS_CUBE_CHECK(jobs && num_jobs >= 1 && num_jobs <= MRGS_PREFILTER_MAX_JOBS, "mrgs_prefilter_apply");
     for (int k = 0; k < num_jobs; ++k) {
@@ -910,7 +910,7 @@ int mrgs_prefilter_apply(const MrgsPrefilterJob* jobs, int32_t num_jobs, int32_t
     int st;
     {
         StageScope sc(backward ? MRGS_STAGE_PREFILTER_BWD : MRGS_STAGE_PREFILTER_FWD, stream, 1);
-        st = launch_prefilter_apply(jobs, num_jobs, stream);
+        st = launch_prefilter_apply(jobs, num_jobs, max_ctas, stream);
     }
     if (st != MRGS_OK) return st;
     MRGS_LAUNCH_OK("prefilter_apply", stream, false);

@@ -153,7 +153,7 @@ void launch_diffuse_cubemap(bool backward, int N, const float* cubemap, float* o
 void launch_texel_table(int N, float* table, cudaStream_t stream);
 int prefilter_patch_count(int N, int G, int PW);
 int launch_prefilter_build(const MrgsPrefilterBuildArgs* a, bool fill, cudaStream_t stream);
-int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, cudaStream_t stream);
+int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, int max_ctas, cudaStream_t stream);
 int launch_mip_pyramid(const float* base3, int res, int num_levels, float* const* levels4, cudaStream_t stream,
                        int* launches);
 void launch_mip_bwd_acc(const float* g_coarse, const float* g_coarse2, float* g_fine, int res_coarse, int accumulate,

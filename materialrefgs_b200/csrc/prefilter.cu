@@ -260,6 +260,7 @@ struct GatherParams {
     GatherJob job[kMaxJobs];
     int warp_end[kMaxJobs];
     int num_jobs;
+    int total_warps;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -304,7 +305,8 @@ __device__ __forceinline__ F3 load_texel(const float* __restrict__ src, size_t i
 }
 
 template <int G, int SS>
-__device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int lane, float* ring, uint64_t* bars) {
+__device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int lane, float* ring, uint64_t* bars,
+                                             uint32_t& phases) {
     constexpr int kRowFloats = G * 32;
     constexpr int kChunkRows = kChunkFloats / kRowFloats;
     int seg = __ldg(j.patch_seg_begin + patch);
@@ -317,6 +319,7 @@ __device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int 
     uint64_t pol = 0;
     if (lane == 0) {
         pol = evict_first_policy();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // (the ring was read by the previous patch)
 #pragma unroll
         for (int c = 0; c < kStages; ++c) {
             if (c < nchunks) {
@@ -335,10 +338,13 @@ __device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int 
         d_next = __ldg(j.seg_desc + seg);
         xs_next = __ldg(j.spans + (size_t)seg * 32 + lane);
     }
+    // `phases` (one bit per stage) is the parity the NEXT completion of each stage's barrier will have; it lives across
+    // the patches of a warp (grid-stride launches), the barriers are initialised once per warp
     int chunk = 0, stage = 0, rpos = 0;
-    uint32_t parity = 0;
-    if (nchunks > 0)
-        while (!mbar_try_wait(bars_s, 0)) {}
+    if (nchunks > 0) {
+        while (!mbar_try_wait(bars_s, phases & 1u)) {}
+        phases ^= 1u;
+    }
     // Measured alternatives (profiles/r02_prefilter.md): issuing the NEXT batch's source loads before consuming the
     // current one (two batches in flight, 64-72 registers) was 15 % slower than this plain 4-deep batch at 60 registers.
     while (seg < seg_end) {
@@ -397,12 +403,11 @@ __device__ __forceinline__ void gather_patch(const GatherJob& j, int patch, int 
                 }
                 ++chunk;
                 rpos = 0;
-                if (++stage == kStages) {
-                    stage = 0;
-                    parity ^= 1u;
+                if (++stage == kStages) stage = 0;
+                if (chunk < nchunks) {
+                    while (!mbar_try_wait(bars_s + stage * 8, (phases >> stage) & 1u)) {}
+                    phases ^= 1u << stage;
                 }
-                if (chunk < nchunks)
-                    while (!mbar_try_wait(bars_s + stage * 8, parity)) {}
             }
         }
     }
@@ -428,27 +433,33 @@ __global__ void __launch_bounds__(kGatherWarps * 32) prefilter_gather_kernel(con
     const int lane = threadIdx.x & 31;
     float* ring = reinterpret_cast<float*>(smem_raw) + wib * kRingFloats;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)kGatherWarps * kRingFloats * sizeof(float)) + wib * kStages;
+    // grid-stride over the patches of all jobs: with the default grid every warp owns exactly one patch; a caller that
+    // wants the gather to run in the BACKGROUND of issue-bound kernels launches fewer CTAs (p.total_warps > grid warps)
+    const int grid_warps = gridDim.x * kGatherWarps;
     if (lane == 0) {
 #pragma unroll
         for (int c = 0; c < kStages; ++c) mbar_init(smem_u32(bars + c), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    const int warp = blockIdx.x * kGatherWarps + wib;
-    int k = 0, first = 0;
-    while (k < p.num_jobs && warp >= p.warp_end[k]) {
-        first = p.warp_end[k];
-        ++k;
-    }
-    if (k >= p.num_jobs) return;
-    const GatherJob& j = p.job[k];
-    const int patch = j.patch_begin + (warp - first);
-    if (j.G == 1) {
-        if (j.src_stride == 4) gather_patch<1, 4>(j, patch, lane, ring, bars);
-        else gather_patch<1, 3>(j, patch, lane, ring, bars);
-    } else {
-        if (j.src_stride == 4) gather_patch<2, 4>(j, patch, lane, ring, bars);
-        else gather_patch<2, 3>(j, patch, lane, ring, bars);
+    uint32_t phases = 0;
+    for (int warp = blockIdx.x * kGatherWarps + wib; warp < p.total_warps; warp += grid_warps) {
+        int k = 0, first = 0;
+        while (k < p.num_jobs && warp >= p.warp_end[k]) {
+            first = p.warp_end[k];
+            ++k;
+        }
+        if (k >= p.num_jobs) break;
+        const GatherJob& j = p.job[k];
+        const int patch = j.patch_begin + (warp - first);
+        if (j.G == 1) {
+            if (j.src_stride == 4) gather_patch<1, 4>(j, patch, lane, ring, bars, phases);
+            else gather_patch<1, 3>(j, patch, lane, ring, bars, phases);
+        } else {
+            if (j.src_stride == 4) gather_patch<2, 4>(j, patch, lane, ring, bars, phases);
+            else gather_patch<2, 3>(j, patch, lane, ring, bars, phases);
+        }
+        __syncwarp();
     }
 }
 
@@ -594,7 +605,7 @@ int launch_prefilter_build(const MrgsPrefilterBuildArgs* a, bool fill, cudaStrea
     return MRGS_OK;
 }
 
-int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, cudaStream_t stream) {
+int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, int max_ctas, cudaStream_t stream) {
     GatherParams p;
     int warps = 0;
     for (int k = 0; k < num_jobs; ++k) {
@@ -622,12 +633,15 @@ int launch_prefilter_apply(const MrgsPrefilterJob* jobs, int num_jobs, cudaStrea
         p.warp_end[k] = warps;
     }
     p.num_jobs = num_jobs;
+    p.total_warps = warps;
     if (warps == 0) return MRGS_OK;
     // > 48 KB of dynamic shared memory is an opt-in per device; setting it is cheap, so no per-process cache
     if (cudaFuncSetAttribute(prefilter_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGatherSmem) !=
         cudaSuccess)
         return MRGS_ERR_CUDA;
-    prefilter_gather_kernel<<<(warps + kGatherWarps - 1) / kGatherWarps, kGatherWarps * 32, kGatherSmem, stream>>>(p);
+    int blocks = (warps + kGatherWarps - 1) / kGatherWarps;
+    if (max_ctas > 0 && max_ctas < blocks) blocks = max_ctas;
+    prefilter_gather_kernel<<<blocks, kGatherWarps * 32, kGatherSmem, stream>>>(p);
     return MRGS_OK;
 }
 

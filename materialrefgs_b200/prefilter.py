@@ -245,9 +245,10 @@ def plan_pair(kind: str, res: int, roughness: float, ct: float | None, device, s
     return fwd, bwd
 
 
-def apply_jobs(jobs, backward: bool, device, shard=None) -> None:
+def apply_jobs(jobs, backward: bool, device, shard=None, max_ctas: int = 0) -> None:
     """jobs: list of (plan, src, src_stride, dst, dst_stride, nan_where_zero or None); ONE launch per 8 jobs,
-    longest tap lists first. shard = (rank, world): only this rank's contiguous share of every plan's patches."""
+    longest tap lists first. shard = (rank, world): only this rank's contiguous share of every plan's patches.
+    max_ctas > 0 caps the grid (background execution next to issue-bound kernels, include/mrgs.h)."""
     lib = _lib.load()
     jobs = sorted(jobs, key=lambda j: -(j[0].rows / max(j[0].patches, 1)))
     if shard is not None:
@@ -270,7 +271,8 @@ def apply_jobs(jobs, backward: bool, device, shard=None) -> None:
             if rng:
                 arr[k].patch_begin, arr[k].patch_end = rng
         with torch.cuda.device(device):
-            _lib.check(lib.mrgs_prefilter_apply(arr, len(chunk), int(backward), _stream(device)), "mrgs_prefilter_apply")
+            _lib.check(lib.mrgs_prefilter_apply(arr, len(chunk), int(backward), int(max_ctas), _stream(device)),
+                       "mrgs_prefilter_apply")
 
 
 def _ptr_array(tensors):
@@ -307,7 +309,7 @@ class MipChain:
 
     _static = None
 
-    def forward(self, base: torch.Tensor, static: bool = False, shard=None):
+    def forward(self, base: torch.Tensor, static: bool = False, shard=None, max_ctas: int = 0):
         """base [6,res,res,3] -> ([prefiltered level l: [6,res>>l,res>>l,3]], diffuse [6,rmin,rmin,3]).
         static: write into the chain's own persistent output buffers (every call returns tensors over the SAME storage),
         which is what consumers captured in a CUDA graph need.
@@ -335,7 +337,7 @@ class MipChain:
             flat.zero_()
         jobs = [(self.spec[l][0], raw[l], 4, levels[l], 3, self.spec[l][0].wsum) for l in range(self.n)]
         jobs.append((self.diff[0], raw[-1], 4, diffuse, 3, None))
-        apply_jobs(jobs, False, dev, None if shard is None else shard[:2])
+        apply_jobs(jobs, False, dev, None if shard is None else shard[:2], max_ctas)
         if shard is not None:
             # every rank filtered its share of every level's patches into the zero-filled buffer: the sum is the chain
             # (x + 0 is exact, so the result equals the unsharded build bit for bit)
@@ -343,7 +345,7 @@ class MipChain:
             dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=shard[2])
         return levels, diffuse
 
-    def backward(self, grad4: torch.Tensor | None, grad_diffuse: torch.Tensor | None, shard=None) -> torch.Tensor:
+    def backward(self, grad4: torch.Tensor | None, grad_diffuse: torch.Tensor | None, shard=None, max_ctas: int = 0) -> torch.Tensor:
         """grad4: [texels,4] gradient of the prefiltered levels (rgb + pad, level after level: the layout of
         EnvLight.level_grad_sink), grad_diffuse [6,rmin,rmin,3]; returns the gradient of the base cubemap."""
         lib = _lib.load()
@@ -368,7 +370,7 @@ class MipChain:
             extra = gflat[self.texels:].view(6, self.sizes[-1], self.sizes[-1], 3)
             jobs.append((self.diff[1], grad_diffuse.contiguous(), 3, extra, 3, None))
         if jobs:
-            apply_jobs(jobs, True, dev, None if shard is None else shard[:2])
+            apply_jobs(jobs, True, dev, None if shard is None else shard[:2], max_ctas)
             if shard is not None:      # the ranks' shares of d(raw levels) (+ the diffuse map's) in ONE collective
                 import torch.distributed as dist
                 dist.all_reduce(gflat, op=dist.ReduceOp.SUM, group=shard[2])
@@ -396,9 +398,9 @@ class _BuildMips(torch.autograd.Function):
     """base -> (level 0, ..., level n-1, diffuse): EnvLight.build_mips (scene/light.py:72-86) as one autograd node."""
 
     @staticmethod
-    def forward(ctx, base, chain: MipChain, static: bool = False, shard=None):
-        levels, diffuse = chain.forward(base, static, shard)
-        ctx.chain, ctx.shard = chain, shard
+    def forward(ctx, base, chain: MipChain, static: bool = False, shard=None, max_ctas: int = 0):
+        levels, diffuse = chain.forward(base, static, shard, max_ctas)
+        ctx.chain, ctx.shard, ctx.max_ctas = chain, shard, max_ctas
         ctx.set_materialize_grads(False)
         if static:      # fresh tensor objects over the persistent storage (an autograd output must not be reused)
             levels, diffuse = [t.view(t.shape) for t in levels], diffuse.view(diffuse.shape)
@@ -409,16 +411,16 @@ class _BuildMips(torch.autograd.Function):
         chain: MipChain = ctx.chain
         g_levels, g_diffuse = grads[:-1], grads[-1]
         if g_diffuse is None and all(g is None for g in g_levels):
-            return None, None, None, None  # e.g. the texel gradients went to EnvLight's sink instead of through autograd
+            return None, None, None, None, None  # e.g. the texel gradients went to EnvLight's sink instead of through autograd
         grad4 = None
         if any(g is not None for g in g_levels):
             grad4 = torch.zeros((chain.texels, 4), dtype=torch.float32, device=chain.device)
             for l, g in enumerate(g_levels):
                 if g is not None:
                     grad4[chain.offsets[l]:chain.offsets[l + 1], :3] = g.reshape(-1, 3)
-        return chain.backward(grad4, g_diffuse, ctx.shard), None, None, None
+        return chain.backward(grad4, g_diffuse, ctx.shard, ctx.max_ctas), None, None, None, None
 
 
-def build_mips(base, chain: MipChain, static: bool = False, shard=None):
-    outs = _BuildMips.apply(base, chain, static, shard)
+def build_mips(base, chain: MipChain, static: bool = False, shard=None, max_ctas: int = 0):
+    outs = _BuildMips.apply(base, chain, static, shard, max_ctas)
     return list(outs[:-1]), outs[-1]

@@ -214,6 +214,8 @@ def shade_surfel(envmap: "EnvLight", rendered_image, rendered_features, allmap, 
     camera exactly as the reference passes `viewpoint_camera.HWK / .R`."""
     cfg = (ray_matrix(HWK, R), np.asarray(R, np.float32), envmap.min_roughness, envmap.max_roughness, srgb,
            getattr(envmap, "level_grad_sink", None), envmap)
+    if getattr(envmap, "_bg_event", None) is not None:
+        envmap.sync()
     levels = envmap.specular
     if cfg[5] is not None:
         # sink mode: the texel gradients go to the sink, not through autograd - the view's autograd graph need not (and,
@@ -349,6 +351,8 @@ class _SurfelShade(torch.autograd.Function):
 def _surfel_colours(envmap: "EnvLight", xyz, albedo, R, T, normal_map, refl_strength, roughness):
     """(diffuse, specular, direct_light) [N,3]: one fused kernel pair for everything per-surfel; the FG pair of the first
     surfel (the reference's `fg[0]`, see _fg_of_first_surfel) is evaluated in torch so its gradient reaches surfel 0."""
+    if getattr(envmap, "_bg_event", None) is not None:
+        envmap.sync()
     rays_o = _camera_origin(R, T, xyz.device)
     w_o0 = safe_normalize(rays_o[None] - xyz[0:1])
     fg = _fg_of_first_surfel(torch.sum(w_o0 * normal_map[0:1], dim=-1, keepdim=True), roughness[0:1])
@@ -410,6 +414,25 @@ class EnvLight(torch.nn.Module):
             return None
         return dist.get_rank(group), dist.get_world_size(group), group
 
+    background = None       # (side stream, CTA cap) set by run_in_background()
+    _bg_event = None
+
+    def run_in_background(self, stream=None, ctas_per_sm: float = 1.0):
+        """build_mips() and flush_level_grads() are HBM-bound gathers that leave most issue slots idle; the tile-blend
+        kernels of the rasterizer are issue-bound and hardly touch HBM. After this call both run on `stream` with a
+        grid capped at ctas_per_sm CTAs per SM, i.e. in the BACKGROUND of the rasterizer kernels the caller enqueues on
+        its own stream meanwhile (forward: the rasterizer forwards of the step's views; backward: their rasterizer
+        backwards). Everything that reads the chain (`shade_surfel`, `__call__`, ...) and the next `build_mips()` call
+        sync() first; call sync() yourself before reading `base.grad`."""
+        dev = self.base.device
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        self.background = (stream if stream is not None else torch.cuda.Stream(device=dev), max(1, int(ctas_per_sm * sms)))
+
+    def sync(self):
+        """Order the current stream after the background build_mips / flush_level_grads, if any."""
+        if self._bg_event is not None:
+            torch.cuda.current_stream(self.base.device).wait_event(self._bg_event)
+
     static_chain = False    # True: build_mips() rewrites the SAME level buffers every time (CUDA-graph consumers, graphs.py)
 
     def chain_roughnesses(self, n):
@@ -423,6 +446,7 @@ class EnvLight(torch.nn.Module):
         other shapes, and chains whose plans exceed the HBM budget, compose the per-level ops like the reference."""
         from . import cubemap as cm
         from . import prefilter as pf
+        self.sync()
         sink = self.level_grad_sink
         if sink is not None and getattr(sink, "_mrgs_pending", False):
             raise RuntimeError("EnvLight.build_mips(): the level-gradient sink holds gradients of the previous chain; "
@@ -437,7 +461,18 @@ class EnvLight(torch.nn.Module):
                 self._chain = pf.get_chain(self.max_res, n, self.chain_roughnesses(n), cutoff, self.base.device)
             except pf.PrefilterTooLarge:
                 self._chain = None
-        if self._chain is not None:
+        if self._chain is not None and self.background is not None:
+            # in the background of whatever the current stream does next (see run_in_background): consumers call sync()
+            side, ctas = self.background
+            main = torch.cuda.current_stream(self.base.device)
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.specular, self.diffuse = pf.build_mips(self.base, self._chain, self.static_chain, self._shard(), ctas)
+                self._bg_event = torch.cuda.Event()
+                self._bg_event.record(side)
+            for t in (*self.specular, self.diffuse):
+                t.record_stream(main)
+        elif self._chain is not None:
             self.specular, self.diffuse = pf.build_mips(self.base, self._chain, self.static_chain, self._shard())
         else:
             self.specular = [self.base]
@@ -490,6 +525,19 @@ class EnvLight(torch.nn.Module):
         sink = self.level_grad_sink
         if sink is None:
             return
+        if self._chain is not None and self.background is not None:
+            side, ctas = self.background
+            main = torch.cuda.current_stream(self.base.device)
+            side.wait_stream(main)       # every shading backward enqueued so far has added into the sink
+            with torch.cuda.stream(side):
+                if self.base.requires_grad:
+                    g = self._chain.backward(sink, None, self._shard(), ctas)
+                    self.base.grad = g if self.base.grad is None else self.base.grad.add_(g)
+                sink.zero_()
+                self._bg_event = torch.cuda.Event()
+                self._bg_event.record(side)
+            sink._mrgs_pending = False
+            return
         if self._chain is not None:
             if self.base.requires_grad:
                 g = self._chain.backward(sink, None, self._shard())
@@ -522,6 +570,7 @@ class EnvLight(torch.nn.Module):
         Differentiable like dr.texture: gradients reach the mip levels (and through build_mips the base cubemap),
         the directions and the roughness."""
         prefix = l.shape[:-1]
+        self.sync()
         if mode == "diffuse":
             levels, rough = [self.diffuse], None
         elif mode == "pure_env":

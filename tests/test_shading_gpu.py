@@ -332,3 +332,37 @@ def test_cubemap_gradient_through_build_mips_sink_equals_autograd():
     assert env.base.grad is None            # nothing reaches the base before the flush
     env.flush_level_grads()
     assert _rel(env.base.grad, 2 * auto) <= 1e-5
+
+
+def test_background_build_mips_and_flush_equal_foreground():
+    """EnvLight.run_in_background(): build_mips / flush_level_grads on a second stream with a capped grid (the
+    grid-stride path of the gather) give the same chain and the same cubemap gradient as the foreground calls."""
+    from materialrefgs_b200.shading import EnvLight, shade_surfel
+    H, W = 96, 128
+    cam = synthetic.orbit_camera(5, 8, W, H)
+    base, feats, allmap = so.synthetic_gbuffer(H, W, device=DEV, seed=4)
+    base = base.requires_grad_(True)
+    bg = torch.zeros(3, device=DEV)
+    w = torch.randn(3, H, W, generator=torch.Generator().manual_seed(23)).to(DEV)
+    res = {}
+    for mode in ("foreground", "background"):
+        env = EnvLight(device=DEV, max_res=128, min_res=16, trainable=True)
+        with torch.no_grad():
+            env.base.copy_(torch.randn(6, 128, 128, 3, generator=torch.Generator().manual_seed(31)).to(DEV))
+        if mode == "background":
+            env.run_in_background(ctas_per_sm=0.25)      # 37 CTAs: every warp strides over many patches
+        env.build_mips()
+        env.enable_level_grad_sink()
+        for _ in range(2):     # two steps: the second build_mips must wait for the first flush
+            env.base.grad = None
+            env.build_mips()
+            out = shade_surfel(env, base, feats, allmap, cam.HWK, cam.R, bg)
+            (out["render"] * w).sum().backward()
+            env.flush_level_grads()
+        env.sync()
+        torch.cuda.synchronize()
+        res[mode] = ([l.detach().clone() for l in env.specular], out["render"].detach().clone(), env.base.grad.clone())
+    for a, b in zip(res["foreground"][0], res["background"][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res["foreground"][1], res["background"][1])
+    assert _rel(res["background"][2], res["foreground"][2]) <= 1e-5     # (texel-gradient atomics are order-dependent)
