@@ -498,7 +498,7 @@ class OursStep(StepBase):
             rs = self.GRS(cam.image_height, cam.image_width, cam.tanfovx, cam.tanfovy, self.bg, 1.0, cam_mats[0], cam_mats[1],
                           wl["sh_degree"], cam_mats[2], False, False)
             rast = self.GR(rs, grad_sink=self.sink)
-            m2 = torch.zeros_like(self.means2D, requires_grad=True) if self.world > 1 else self.means2D
+            m2 = self.means2D
             _, color, feat, radii, allmap = rast(means3D=L["means3D"], means2D=m2, opacities=L["opacities"], shs=L["shs"],
                                                  features=L["features"], scales=L["scales"], rotations=L["rotations"])
             if getattr(rast, "num_rendered", None):
@@ -517,25 +517,16 @@ class OursStep(StepBase):
                 self.taken, self.last_view = slot, view
                 self._e2e_readback(i & 1, v, loss)
         # every view's texel gradients are in the sink: the cubemap's backward starts now, under the rasterizer backwards
-        if self.world > 1:
-            self.sink_work = self.arena.allreduce_extra_async()
-            with torch.cuda.stream(self.env.background[0]):
-                self.env.background[0].wait_stream(torch.cuda.current_stream(self.dev))
-                self.arena.wait(self.sink_work)
-            self.sink_work = None
+        # (single GPU only, see __init__: no collective is involved)
         self.env.flush_level_grads()
         for (view, cam, up, color, feat, allmap, radii, m2, slot), g in zip(gbuf, grads):
             m2.grad = None
             torch.autograd.backward([color, feat, allmap], list(g))
-            if self.world > 1:
-                self.arena.accumulate_view({}, m2.grad, radii)
         total = None
         if e2e:
             self.result_events[i & 1].record(self.copy_stream)
             total = self._e2e_consume((i & 1) ^ 1)
             self.result_pending[i & 1] = True
-        if self.world > 1:
-            self.inflight = self.arena.allreduce_main_async()
         return total
 
     def measure_costs(self):
